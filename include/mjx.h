@@ -1,0 +1,167 @@
+/*
+ * mjx.h -- kernel-level C-ABI of the B200 (sm_100a) compositing engine, libmjx.so.
+ *
+ * This is the drop-in boundary for the hot path: plain pointers, sizes and ints, no torch or
+ * C++ types.  Each entry point names the reference code it replaces.  The host library
+ * (libmodjpeg.so, include/libmodjpeg.h) calls these from mj_compose() / mj_effect_*(); a
+ * batch host (bench.py, a server) calls the *_batch_device / *_batch_host forms directly.
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - A coefficient plane is int16 [rows][stride_blocks][64], natural order (index 8*v + u),
+ *     exactly libjpeg's JBLOCKROW layout (reference: src/compose.c:269-274).
+ *   - All calls are asynchronous on the context's stream unless they take host pointers;
+ *     host-pointer calls return when the host buffers hold the result (the reference's
+ *     synchronous semantics).
+ *   - Return value: MJX_OK or an MJX_ERR_* code; mjx_ctx_last_error() has the CUDA text.
+ *   - There is no CPU fallback.  Without a usable CUDA device every compute entry point
+ *     returns MJX_ERR_DEVICE.
+ */
+#ifndef MJX_H
+#define MJX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MJX_OK              0
+#define MJX_ERR_MEMORY      1  /* == MJ_ERR_MEMORY */
+#define MJX_ERR_ARG         2  /* == MJ_ERR_NULL_DATA */
+#define MJX_ERR_UNSUPPORTED 6  /* == MJ_ERR_ENCODE_JPEG: a dropon->target conversion libjpeg rejects */
+#define MJX_ERR_DEVICE      10 /* == MJ_ERR_DEVICE: no device, or a CUDA call failed */
+
+#define MJX_MAX_COMPONENTS 4
+
+/* dropon pixel formats after ingest (== MJ_COLORSPACE_RGB / _GRAYSCALE / _YCC) */
+#define MJX_CS_RGB       1
+#define MJX_CS_GRAYSCALE 3
+#define MJX_CS_YCC       5
+
+/* block classes of a compiled dropon */
+#define MJX_CLS_T      0
+#define MJX_CLS_U      1
+#define MJX_CLS_OPAQUE 2
+#define MJX_CLS_G      3
+
+typedef struct mjx_ctx    mjx_ctx;    /* one device + stream + staging pools; not shareable between threads */
+typedef struct mjx_dropon mjx_dropon; /* a compiled dropon resident in HBM; immutable, shareable between ctxs on one device */
+
+/* component layout of the target JPEG: what mj_compile_dropon receives as
+ * (J_COLOR_SPACE colorspace, mj_sampling_t *sampling) (reference: src/dropon.c:325) */
+typedef struct {
+    int colorspace; /* J_COLOR_SPACE: 1 GRAYSCALE, 2 RGB, 3 YCbCr */
+    int ncomp;
+    int h_samp[MJX_MAX_COMPONENTS];
+    int v_samp[MJX_MAX_COMPONENTS];
+} mjx_layout_t;
+
+/* result of the placement arithmetic of mj_compose (reference: src/compose.c:42-172) */
+typedef struct {
+    int visible; /* 0: nothing of the dropon lies on the image (reference returns MJ_OK, compose.c:136) */
+    int crop_x, crop_y, crop_w, crop_h;
+    int blockoffset_x, blockoffset_y;
+    int block_x, block_y; /* origin on the image in MCUs */
+} mjx_geometry_t;
+
+/* one image of a device-resident batch; an array of these lives in device memory */
+typedef struct {
+    uint64_t plane[MJX_MAX_COMPONENTS];         /* device address of block (0,0) of each component plane */
+    int32_t  stride_blocks[MJX_MAX_COMPONENTS]; /* blocks per plane row (libjpeg's virtual width) */
+    int32_t  rows[MJX_MAX_COMPONENTS];          /* plane rows in blocks (virtual height) */
+    int32_t  wreal[MJX_MAX_COMPONENTS];         /* width_in_blocks  (effects touch real blocks only) */
+    int32_t  hreal[MJX_MAX_COMPONENTS];         /* height_in_blocks */
+    uint16_t q[MJX_MAX_COMPONENTS][64];         /* quantisation tables, natural order */
+} mjx_image_desc_t;
+
+/* the same for host-resident planes (contiguous [rows][stride_blocks][64] per component) */
+typedef struct {
+    int16_t        *plane[MJX_MAX_COMPONENTS];
+    int32_t         stride_blocks[MJX_MAX_COMPONENTS];
+    int32_t         rows[MJX_MAX_COMPONENTS];
+    int32_t         wreal[MJX_MAX_COMPONENTS];
+    int32_t         hreal[MJX_MAX_COMPONENTS];
+    const uint16_t *q[MJX_MAX_COMPONENTS];
+} mjx_host_image_t;
+
+/* one step of an effect pipeline (K3).  Steps are applied in order to every block. */
+#define MJX_FX_ZERO     1 /* all 64 coefficients of component `comp` := 0   (mj_effect_grayscale, src/effect.c:28) */
+#define MJX_FX_PIXELATE 2 /* coefficients 1..63 of component `comp` := 0    (mj_effect_pixelate,  src/effect.c:70) */
+#define MJX_FX_ADD_DC   3 /* DC of `comp`: dequantise, += value, clamp +-2047, requantise (tint/luminance, src/effect.c:116,185) */
+typedef struct {
+    int op;
+    int comp;
+    int value;
+} mjx_effect_op_t;
+
+/* ---- context ---------------------------------------------------------------------- */
+int         mjx_device_count(void);
+int         mjx_ctx_create(mjx_ctx **ctx, int device);
+void        mjx_ctx_destroy(mjx_ctx *ctx);
+int         mjx_ctx_set_stream(mjx_ctx *ctx, void *cuda_stream); /* borrow a caller-owned cudaStream_t (NULL: back to the ctx's own) */
+void       *mjx_ctx_stream(mjx_ctx *ctx);
+int         mjx_ctx_sync(mjx_ctx *ctx);
+const char *mjx_ctx_last_error(mjx_ctx *ctx);
+long long   mjx_ctx_kernel_launches(mjx_ctx *ctx); /* kernels launched through this ctx so far */
+
+/* device / pinned-host memory for callers without their own allocator */
+int  mjx_device_alloc(mjx_ctx *ctx, void **ptr, size_t bytes);
+void mjx_device_free(mjx_ctx *ctx, void *ptr);
+int  mjx_host_alloc(mjx_ctx *ctx, void **ptr, size_t bytes); /* page-locked */
+void mjx_host_free(mjx_ctx *ctx, void *ptr);
+int  mjx_copy_h2d(mjx_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes); /* async on the ctx stream */
+int  mjx_copy_d2h(mjx_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+
+/* ---- A1: placement arithmetic, host only (replaces src/compose.c:42-172) ------------- */
+void mjx_geometry(int image_width, int image_height, int h_factor, int v_factor, int dropon_width, int dropon_height,
+                  unsigned int align, int offset_x, int offset_y, mjx_geometry_t *out);
+
+/* ---- K1: dropon compile (replaces mj_compile_dropon, src/dropon.c:325-576, and the two
+ *      libjpeg encode + decode round trips it makes through src/image.c:257-347) -------- */
+int  mjx_dropon_compile(mjx_ctx *ctx, mjx_dropon **out,
+                        const uint8_t *image3, const uint8_t *alpha3, /* mj_dropon_t.image / .alpha: 3 bytes per pixel */
+                        int width, int height, int dropon_colorspace, /* MJX_CS_* */
+                        const mjx_layout_t *layout,
+                        int blockoffset_x, int blockoffset_y, int crop_x, int crop_y, int crop_w, int crop_h,
+                        int pixels_on_device); /* 0: image3/alpha3 are host pointers; 1: device pointers */
+/* build a compiled dropon from host-side coefficient planes D[c], W[c] ([hb][wb][64] int16, W with
+ * DC already += 1024) -- lets K2 be driven with a dropon compiled elsewhere (e.g. by the oracle) */
+int  mjx_dropon_from_coefficients(mjx_ctx *ctx, mjx_dropon **out, const mjx_layout_t *layout,
+                                  const int *wb, const int *hb, const int16_t *const *D, const int16_t *const *W);
+void mjx_dropon_free(mjx_dropon *d);
+int  mjx_dropon_ncomp(const mjx_dropon *d);
+int  mjx_dropon_dims(const mjx_dropon *d, int comp, int *wb, int *hb);
+long long mjx_dropon_blocks(const mjx_dropon *d); /* all components */
+/* copy component `comp` back: D, W int16 [hb][wb][64]; cls uint8 [hb][wb] (any may be NULL) */
+int  mjx_dropon_download(mjx_ctx *ctx, const mjx_dropon *d, int comp, int16_t *D, int16_t *W, uint8_t *cls);
+/* counts[MJX_CLS_*] summed over all components */
+int  mjx_dropon_class_counts(mjx_ctx *ctx, const mjx_dropon *d, long long counts[4]);
+
+/* ---- K2: masked blend (replaces mj_compose_with_mask + mj_convolve, src/compose.c:237-342,
+ *      src/convolve.c:29-1099) ---------------------------------------------------------- */
+/* n images resident in HBM, one compiled dropon at MCU position (block_x, block_y) on each */
+int mjx_compose_batch_device(mjx_ctx *ctx, const mjx_image_desc_t *items_dev, int n, const mjx_dropon *d,
+                             int block_x, int block_y);
+/* n images in host memory: region under the dropon is staged H2D, blended, staged back */
+int mjx_compose_batch_host(mjx_ctx *ctx, const mjx_host_image_t *items, int n, const mjx_dropon *d,
+                           int block_x, int block_y);
+/* one image given as libjpeg row pointers: rows[c][l] -> block (block_y*v_c + l, block_x*h_c) of component c,
+ * l in [0, hb_c) (what access_virt_barray returns, reference: src/compose.c:269) */
+int mjx_compose_rows_host(mjx_ctx *ctx, int ncomp, int16_t *const *const *rows, const uint16_t *const *q,
+                          const mjx_dropon *d);
+
+/* ---- K3: coefficient effects (replaces src/effect.c:28-222) --------------------------- */
+int mjx_effects_batch_device(mjx_ctx *ctx, const mjx_image_desc_t *items_dev, int n, int ncomp,
+                             const mjx_effect_op_t *ops, int nops);
+/* one image as libjpeg row pointers: rows[c][l] -> block (l, 0), l in [0, hreal[c]); only the
+ * components named by ops are staged */
+int mjx_effects_rows_host(mjx_ctx *ctx, int ncomp, int16_t *const *const *rows, const int *wreal, const int *hreal,
+                          const uint16_t *const *q, const mjx_effect_op_t *ops, int nops);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* MJX_H */

@@ -1,0 +1,37 @@
+/*
+ * mjx_host.h -- additive host-side entry points of libmodjpeg.so (beyond the 16 functions of
+ * libmodjpeg.h): flat access to the coefficient planes of a decoded JPEG, so that a batch host
+ * (bench.py, a server front end) can move them to HBM and drive the kernel-level C-ABI (mjx.h)
+ * itself.  They go through cinfo.mem->access_virt_barray exactly like the reference's own loops
+ * (reference: src/compose.c:269, src/effect.c:48).  They expect an mj_jpeg_t filled by this
+ * library's mj_read_jpeg_* (its error trap lives in the struct's libjpeg pool).
+ */
+#ifndef MJX_HOST_H
+#define MJX_HOST_H
+
+#include "libmodjpeg.h"
+#include "mjx.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* info[0..5] = num_components, jpeg_color_space, width, height, max_h_samp_factor, max_v_samp_factor */
+int mjx_jpeg_image_info(mj_jpeg_t *m, int *info);
+/* info[0..5] = width_in_blocks, height_in_blocks, h_samp_factor, v_samp_factor, virtual width, virtual height */
+int mjx_jpeg_component_info(mj_jpeg_t *m, int c, int *info);
+int mjx_jpeg_qtable(mj_jpeg_t *m, int c, unsigned short *q64);
+/* copy a whole plane ([virtual height][virtual width][64] int16) out of / into libjpeg's arrays */
+int mjx_jpeg_export_plane(mj_jpeg_t *m, int c, short *dst);
+int mjx_jpeg_import_plane(mj_jpeg_t *m, int c, const short *src);
+/* the target layout of a decoded JPEG, as K1 wants it */
+int mjx_jpeg_layout(mj_jpeg_t *m, mjx_layout_t *layout);
+/* the calling thread's engine context (created on first use; device from $MJX_DEVICE, default 0).
+ * Returns NULL and prints one line to stderr when no CUDA device is usable. */
+mjx_ctx *mjx_host_ctx(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

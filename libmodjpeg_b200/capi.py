@@ -1,0 +1,546 @@
+"""ctypes bindings of the two product libraries.
+
+* ``Engine``   -- libmjx.so, the kernel-level C-ABI (include/mjx.h): compiled dropons (K1),
+  masked blend (K2) and effects (K3) on device-resident or host planes.
+* ``ModJpeg``  -- libmodjpeg.so, the reference's public API (include/libmodjpeg.h) mirrored in
+  Python with the reference's names (``read_jpeg_from_memory``, ``compose``, ``effect_tint`` ...).
+
+The libraries are built in-tree by ``libmodjpeg_b200.build``; importing this module never
+builds and never falls back to a CPU path: a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIBDIR = os.path.join(PKG, "lib")
+LIBMJX = os.path.join(LIBDIR, "libmjx.so")
+LIBMODJPEG = os.path.join(LIBDIR, "libmodjpeg.so")
+
+MAX_COMPONENTS = 4
+OK, ERR_MEMORY, ERR_ARG, ERR_UNSUPPORTED, ERR_DEVICE = 0, 1, 2, 6, 10
+CS_RGB, CS_RGBA, CS_GRAYSCALE, CS_GRAYSCALEA, CS_YCC, CS_YCCA = 1, 2, 3, 4, 5, 6
+ALIGN_LEFT, ALIGN_RIGHT, ALIGN_TOP, ALIGN_BOTTOM, ALIGN_CENTER = 1, 2, 4, 8, 16
+JCS_GRAYSCALE, JCS_RGB, JCS_YCbCr = 1, 2, 3
+CLS_T, CLS_U, CLS_OPAQUE, CLS_G = 0, 1, 2, 3
+FX_ZERO, FX_PIXELATE, FX_ADD_DC = 1, 2, 3
+OPTION_NONE, OPTION_OPTIMIZE, OPTION_PROGRESSIVE, OPTION_ARITHMETRIC = 0, 1, 2, 4
+
+
+class MjxError(RuntimeError):
+    def __init__(self, code: int, what: str):
+        super().__init__(f"{what}: error {code}")
+        self.code = code
+
+
+class Layout(C.Structure):
+    _fields_ = [("colorspace", C.c_int), ("ncomp", C.c_int), ("h_samp", C.c_int * 4), ("v_samp", C.c_int * 4)]
+
+    @classmethod
+    def make(cls, colorspace: int, samp) -> "Layout":
+        L = cls()
+        L.colorspace = colorspace
+        L.ncomp = len(samp)
+        for i, (h, v) in enumerate(samp):
+            L.h_samp[i] = h
+            L.v_samp[i] = v
+        return L
+
+
+class Geometry(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("visible", "crop_x", "crop_y", "crop_w", "crop_h",
+                                        "blockoffset_x", "blockoffset_y", "block_x", "block_y")]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class ImageDesc(C.Structure):
+    """mjx_image_desc_t -- one image of a device-resident batch (608 bytes)."""
+    _fields_ = [("plane", C.c_uint64 * 4), ("stride_blocks", C.c_int32 * 4), ("rows", C.c_int32 * 4),
+                ("wreal", C.c_int32 * 4), ("hreal", C.c_int32 * 4), ("q", (C.c_uint16 * 64) * 4)]
+
+
+class HostImage(C.Structure):
+    _fields_ = [("plane", C.c_void_p * 4), ("stride_blocks", C.c_int32 * 4), ("rows", C.c_int32 * 4),
+                ("wreal", C.c_int32 * 4), ("hreal", C.c_int32 * 4), ("q", C.c_void_p * 4)]
+
+
+class EffectOp(C.Structure):
+    _fields_ = [("op", C.c_int), ("comp", C.c_int), ("value", C.c_int)]
+
+
+IMAGE_DESC_DTYPE = np.dtype([("plane", "<u8", 4), ("stride_blocks", "<i4", 4), ("rows", "<i4", 4),
+                             ("wreal", "<i4", 4), ("hreal", "<i4", 4), ("q", "<u2", (4, 64))])
+assert IMAGE_DESC_DTYPE.itemsize == C.sizeof(ImageDesc) == 608
+
+_lib_mjx = None
+_lib_mj = None
+
+
+def load_mjx() -> C.CDLL:
+    """Load libmjx.so.  Raises if it has not been built -- there is no fallback."""
+    global _lib_mjx
+    if _lib_mjx is not None:
+        return _lib_mjx
+    if not os.path.exists(LIBMJX):
+        raise FileNotFoundError(f"{LIBMJX} is missing: run `python -m libmodjpeg_b200.build` (no CPU fallback exists)")
+    L = C.CDLL(LIBMJX, mode=C.RTLD_GLOBAL)
+    vp, ip = C.c_void_p, C.POINTER(C.c_int)
+    L.mjx_device_count.restype = C.c_int
+    L.mjx_ctx_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.mjx_ctx_destroy.argtypes = [vp]
+    L.mjx_ctx_destroy.restype = None
+    L.mjx_ctx_set_stream.argtypes = [vp, vp]
+    L.mjx_ctx_stream.argtypes = [vp]
+    L.mjx_ctx_stream.restype = vp
+    L.mjx_ctx_sync.argtypes = [vp]
+    L.mjx_ctx_last_error.argtypes = [vp]
+    L.mjx_ctx_last_error.restype = C.c_char_p
+    L.mjx_ctx_kernel_launches.argtypes = [vp]
+    L.mjx_ctx_kernel_launches.restype = C.c_longlong
+    L.mjx_device_alloc.argtypes = [vp, C.POINTER(vp), C.c_size_t]
+    L.mjx_device_free.argtypes = [vp, vp]
+    L.mjx_device_free.restype = None
+    L.mjx_host_alloc.argtypes = [vp, C.POINTER(vp), C.c_size_t]
+    L.mjx_host_free.argtypes = [vp, vp]
+    L.mjx_host_free.restype = None
+    L.mjx_copy_h2d.argtypes = [vp, vp, vp, C.c_size_t]
+    L.mjx_copy_d2h.argtypes = [vp, vp, vp, C.c_size_t]
+    L.mjx_geometry.argtypes = [C.c_int] * 6 + [C.c_uint, C.c_int, C.c_int, C.POINTER(Geometry)]
+    L.mjx_geometry.restype = None
+    L.mjx_dropon_compile.argtypes = [vp, C.POINTER(vp), vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(Layout)] + \
+        [C.c_int] * 6 + [C.c_int]
+    L.mjx_dropon_from_coefficients.argtypes = [vp, C.POINTER(vp), C.POINTER(Layout), ip, ip, C.POINTER(vp), C.POINTER(vp)]
+    L.mjx_dropon_free.argtypes = [vp]
+    L.mjx_dropon_free.restype = None
+    L.mjx_dropon_ncomp.argtypes = [vp]
+    L.mjx_dropon_dims.argtypes = [vp, C.c_int, ip, ip]
+    L.mjx_dropon_blocks.argtypes = [vp]
+    L.mjx_dropon_blocks.restype = C.c_longlong
+    L.mjx_dropon_download.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+    L.mjx_dropon_class_counts.argtypes = [vp, vp, C.POINTER(C.c_longlong)]
+    L.mjx_compose_batch_device.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int]
+    L.mjx_compose_batch_host.argtypes = [vp, C.POINTER(HostImage), C.c_int, vp, C.c_int, C.c_int]
+    L.mjx_compose_rows_host.argtypes = [vp, C.c_int, vp, vp, vp]
+    L.mjx_effects_batch_device.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(EffectOp), C.c_int]
+    L.mjx_effects_rows_host.argtypes = [vp, C.c_int, vp, ip, ip, vp, C.POINTER(EffectOp), C.c_int]
+    _lib_mjx = L
+    return L
+
+
+def geometry(image_w, image_h, h_factor, v_factor, dropon_w, dropon_h, align, offset_x=0, offset_y=0) -> dict:
+    """Placement arithmetic of mj_compose (reference: src/compose.c:42-172); host only, no GPU needed."""
+    g = Geometry()
+    load_mjx().mjx_geometry(image_w, image_h, h_factor, v_factor, dropon_w, dropon_h, align, offset_x, offset_y, C.byref(g))
+    return g.as_dict()
+
+
+class CompiledDropon:
+    """A compiled dropon resident in HBM (mjx_dropon)."""
+
+    def __init__(self, engine: "Engine", handle: int):
+        self.engine = engine
+        self.handle = C.c_void_p(handle)
+
+    @property
+    def ncomp(self) -> int:
+        return self.engine.lib.mjx_dropon_ncomp(self.handle)
+
+    def dims(self, c: int) -> tuple[int, int]:
+        wb, hb = C.c_int(), C.c_int()
+        self.engine._check(self.engine.lib.mjx_dropon_dims(self.handle, c, C.byref(wb), C.byref(hb)), "mjx_dropon_dims")
+        return wb.value, hb.value
+
+    @property
+    def blocks(self) -> int:
+        return self.engine.lib.mjx_dropon_blocks(self.handle)
+
+    def class_counts(self) -> dict:
+        a = (C.c_longlong * 4)()
+        self.engine._check(self.engine.lib.mjx_dropon_class_counts(self.engine.ctx, self.handle, a), "mjx_dropon_class_counts")
+        return {"T": a[0], "U": a[1], "OPAQUE": a[2], "G": a[3]}
+
+    def download(self, c: int):
+        wb, hb = self.dims(c)
+        D = np.zeros((hb, wb, 64), np.int16)
+        W = np.zeros((hb, wb, 64), np.int16)
+        cls = np.zeros((hb, wb), np.uint8)
+        self.engine._check(self.engine.lib.mjx_dropon_download(self.engine.ctx, self.handle, c, D.ctypes.data, W.ctypes.data,
+                                                               cls.ctypes.data), "mjx_dropon_download")
+        return D, W, cls
+
+    def free(self) -> None:
+        if self.handle:
+            self.engine.lib.mjx_dropon_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One mjx_ctx: a device, a stream and staging pools.  Not shareable between threads."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_mjx()
+        ctx = C.c_void_p()
+        rv = self.lib.mjx_ctx_create(C.byref(ctx), device)
+        if rv != OK:
+            raise MjxError(rv, f"mjx_ctx_create(device={device}): no usable CUDA device "
+                               f"({self.lib.mjx_device_count()} visible); the engine has no CPU fallback")
+        self.ctx = ctx
+        self.device = device
+
+    def close(self) -> None:
+        if getattr(self, "ctx", None):
+            self.lib.mjx_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rv: int, what: str) -> None:
+        if rv != OK:
+            msg = self.lib.mjx_ctx_last_error(self.ctx)
+            raise MjxError(rv, f"{what} [{msg.decode() if msg else ''}]")
+
+    # ---- context ----------------------------------------------------------------------
+    def set_stream(self, cuda_stream: int | None) -> None:
+        self._check(self.lib.mjx_ctx_set_stream(self.ctx, C.c_void_p(cuda_stream or 0)), "mjx_ctx_set_stream")
+
+    @property
+    def stream(self) -> int:
+        return self.lib.mjx_ctx_stream(self.ctx) or 0
+
+    def sync(self) -> None:
+        self._check(self.lib.mjx_ctx_sync(self.ctx), "mjx_ctx_sync")
+
+    @property
+    def kernel_launches(self) -> int:
+        return self.lib.mjx_ctx_kernel_launches(self.ctx)
+
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.mjx_device_alloc(self.ctx, C.byref(p), nbytes), "mjx_device_alloc")
+        return p.value
+
+    def device_free(self, ptr: int) -> None:
+        self.lib.mjx_device_free(self.ctx, C.c_void_p(ptr))
+
+    def host_alloc(self, nbytes: int, dtype=np.uint8) -> np.ndarray:
+        """Page-locked host memory as a numpy array (freed with host_free)."""
+        p = C.c_void_p()
+        self._check(self.lib.mjx_host_alloc(self.ctx, C.byref(p), nbytes), "mjx_host_alloc")
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        a = np.frombuffer(buf, dtype=np.uint8).view(dtype)
+        return a
+
+    def host_free(self, a: np.ndarray) -> None:
+        self.lib.mjx_host_free(self.ctx, C.c_void_p(a.ctypes.data))
+
+    def copy_h2d(self, dst_dev: int, src: np.ndarray) -> None:
+        self._check(self.lib.mjx_copy_h2d(self.ctx, C.c_void_p(dst_dev), C.c_void_p(src.ctypes.data), src.nbytes), "mjx_copy_h2d")
+
+    def copy_d2h(self, dst: np.ndarray, src_dev: int) -> None:
+        self._check(self.lib.mjx_copy_d2h(self.ctx, C.c_void_p(dst.ctypes.data), C.c_void_p(src_dev), dst.nbytes), "mjx_copy_d2h")
+
+    # ---- K1 -----------------------------------------------------------------------------
+    def dropon_compile(self, image3, alpha3, dropon_cs: int, layout: Layout, blockoffset=(0, 0), crop=None,
+                       device_pixels: tuple[int, int, int, int] | None = None) -> CompiledDropon:
+        """mj_compile_dropon on the GPU.  image3/alpha3: uint8 [h][w][3] host arrays, or pass
+        device_pixels=(image_ptr, alpha_ptr, width, height) for pixels already in HBM."""
+        if device_pixels is not None:
+            ip, ap, w, h = device_pixels
+            on_dev = 1
+        else:
+            image3 = np.ascontiguousarray(image3, np.uint8)
+            alpha3 = np.ascontiguousarray(alpha3, np.uint8)
+            h, w = image3.shape[:2]
+            ip, ap, on_dev = image3.ctypes.data, alpha3.ctypes.data, 0
+        cx, cy, cw, ch = crop if crop is not None else (0, 0, w, h)
+        out = C.c_void_p()
+        rv = self.lib.mjx_dropon_compile(self.ctx, C.byref(out), C.c_void_p(ip), C.c_void_p(ap), w, h, dropon_cs,
+                                         C.byref(layout), blockoffset[0], blockoffset[1], cx, cy, cw, ch, on_dev)
+        self._check(rv, "mjx_dropon_compile")
+        return CompiledDropon(self, out.value)
+
+    def dropon_from_coefficients(self, layout: Layout, D: list[np.ndarray], W: list[np.ndarray]) -> CompiledDropon:
+        n = layout.ncomp
+        D = [np.ascontiguousarray(a, np.int16) for a in D]
+        W = [np.ascontiguousarray(a, np.int16) for a in W]
+        wb = (C.c_int * 4)(*[a.shape[1] for a in D] + [0] * (4 - n))
+        hb = (C.c_int * 4)(*[a.shape[0] for a in D] + [0] * (4 - n))
+        Dp = (C.c_void_p * 4)(*[a.ctypes.data for a in D] + [None] * (4 - n))
+        Wp = (C.c_void_p * 4)(*[a.ctypes.data for a in W] + [None] * (4 - n))
+        out = C.c_void_p()
+        self._check(self.lib.mjx_dropon_from_coefficients(self.ctx, C.byref(out), C.byref(layout), wb, hb, Dp, Wp),
+                    "mjx_dropon_from_coefficients")
+        return CompiledDropon(self, out.value)
+
+    # ---- K2 -----------------------------------------------------------------------------
+    def compose_batch_device(self, items_dev: int, n: int, dropon: CompiledDropon, block_x: int, block_y: int) -> None:
+        self._check(self.lib.mjx_compose_batch_device(self.ctx, C.c_void_p(items_dev), n, dropon.handle, block_x, block_y),
+                    "mjx_compose_batch_device")
+
+    def compose_batch_host(self, items, n: int, dropon: CompiledDropon, block_x: int, block_y: int) -> None:
+        self._check(self.lib.mjx_compose_batch_host(self.ctx, items, n, dropon.handle, block_x, block_y),
+                    "mjx_compose_batch_host")
+
+    def compose_planes_host(self, planes: list[np.ndarray], qtables: list[np.ndarray], dropon: CompiledDropon,
+                            block_x: int, block_y: int) -> None:
+        """One image given as flat host planes [rows][cols][64] int16, blended in place."""
+        item, keep = make_host_image(planes, qtables)
+        arr = (HostImage * 1)(item)
+        self.compose_batch_host(arr, 1, dropon, block_x, block_y)
+        del keep
+
+    # ---- K3 -----------------------------------------------------------------------------
+    def effects_batch_device(self, items_dev: int, n: int, ncomp: int, ops: list[tuple[int, int, int]]) -> None:
+        arr = (EffectOp * max(1, len(ops)))(*[EffectOp(*o) for o in ops])
+        self._check(self.lib.mjx_effects_batch_device(self.ctx, C.c_void_p(items_dev), n, ncomp, arr, len(ops)),
+                    "mjx_effects_batch_device")
+
+
+def make_host_image(planes: list[np.ndarray], qtables: list[np.ndarray], real_dims=None):
+    """HostImage over flat numpy planes; returns (struct, keepalive)."""
+    it = HostImage()
+    keep = []
+    for c, (p, q) in enumerate(zip(planes, qtables)):
+        assert p.dtype == np.int16 and p.flags.c_contiguous and p.ndim == 3 and p.shape[2] == 64
+        q = np.ascontiguousarray(q, np.uint16)
+        keep += [p, q]
+        it.plane[c] = p.ctypes.data
+        it.stride_blocks[c] = p.shape[1]
+        it.rows[c] = p.shape[0]
+        it.wreal[c] = real_dims[c][0] if real_dims else p.shape[1]
+        it.hreal[c] = real_dims[c][1] if real_dims else p.shape[0]
+        it.q[c] = q.ctypes.data
+    return it, keep
+
+
+def make_image_descs(plane_ptrs, strides, rows, qtables, real_dims=None) -> np.ndarray:
+    """Array of mjx_image_desc_t for a device-resident batch.
+    plane_ptrs: [n][ncomp] device addresses; strides/rows: [ncomp]; qtables: [n][ncomp][64] or [ncomp][64]."""
+    n = len(plane_ptrs)
+    ncomp = len(strides)
+    a = np.zeros(n, IMAGE_DESC_DTYPE)
+    q = np.asarray(qtables, np.uint16)
+    for c in range(ncomp):
+        a["plane"][:, c] = [p[c] for p in plane_ptrs]
+        a["stride_blocks"][:, c] = strides[c]
+        a["rows"][:, c] = rows[c]
+        a["wreal"][:, c] = real_dims[c][0] if real_dims else strides[c]
+        a["hreal"][:, c] = real_dims[c][1] if real_dims else rows[c]
+        a["q"][:, c, :] = q[:, c, :] if q.ndim == 3 else q[c]
+    return a
+
+
+# --------------------------------------------------------------------------------------
+# the public API (include/libmodjpeg.h) mirrored in Python
+# --------------------------------------------------------------------------------------
+
+
+class _DroponStruct(C.Structure):
+    _fields_ = [("image", C.POINTER(C.c_uint8)), ("alpha", C.POINTER(C.c_uint8)), ("width", C.c_int), ("height", C.c_int),
+                ("colorspace", C.c_int), ("blend", C.c_int)]
+
+
+def load_modjpeg() -> C.CDLL:
+    global _lib_mj
+    if _lib_mj is not None:
+        return _lib_mj
+    load_mjx()
+    if not os.path.exists(LIBMODJPEG):
+        raise FileNotFoundError(f"{LIBMODJPEG} is missing: run `python -m libmodjpeg_b200.build`")
+    L = C.CDLL(LIBMODJPEG)
+    vp = C.c_void_p
+    L.mj_init_jpeg.argtypes = [vp]
+    L.mj_init_jpeg.restype = None
+    L.mj_free_jpeg.argtypes = [vp]
+    L.mj_free_jpeg.restype = None
+    L.mj_read_jpeg_from_memory.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_size_t]
+    L.mj_read_jpeg_from_file.argtypes = [vp, C.c_char_p, C.c_size_t]
+    L.mj_write_jpeg_to_memory.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.c_int]
+    L.mj_write_jpeg_to_file.argtypes = [vp, C.c_char_p, C.c_int]
+    L.mj_init_dropon.argtypes = [vp]
+    L.mj_init_dropon.restype = None
+    L.mj_free_dropon.argtypes = [vp]
+    L.mj_free_dropon.restype = None
+    L.mj_read_dropon_from_raw.argtypes = [vp, C.c_char_p, C.c_uint, C.c_int, C.c_int, C.c_short]
+    L.mj_read_dropon_from_memory.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_short]
+    L.mj_read_dropon_from_file.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_short]
+    L.mj_compose.argtypes = [vp, vp, C.c_uint, C.c_int, C.c_int]
+    L.mj_effect_grayscale.argtypes = [vp]
+    L.mj_effect_pixelate.argtypes = [vp]
+    L.mj_effect_tint.argtypes = [vp, C.c_int, C.c_int]
+    L.mj_effect_luminance.argtypes = [vp, C.c_int]
+    L.mjx_jpeg_image_info.argtypes = [vp, C.POINTER(C.c_int)]
+    L.mjx_jpeg_component_info.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
+    L.mjx_jpeg_qtable.argtypes = [vp, C.c_int, vp]
+    L.mjx_jpeg_export_plane.argtypes = [vp, C.c_int, vp]
+    L.mjx_jpeg_import_plane.argtypes = [vp, C.c_int, vp]
+    L.mjx_jpeg_layout.argtypes = [vp, C.POINTER(Layout)]
+    L.mjx_host_ctx.argtypes = []
+    L.mjx_host_ctx.restype = vp
+    _lib_mj = L
+    return L
+
+
+_libc = C.CDLL(None)
+_libc.free.argtypes = [C.c_void_p]
+_libc.free.restype = None
+
+
+class Jpeg:
+    """mj_jpeg_t: a decoded JPEG (libjpeg state + coefficient arrays)."""
+
+    SIZE = 1024  # >= sizeof(mj_jpeg_t) == 696 with the ABI-62 libjpeg
+
+    def __init__(self):
+        self.lib = load_modjpeg()
+        self.buf = C.create_string_buffer(self.SIZE)
+        self.ptr = C.cast(self.buf, C.c_void_p)
+        self.lib.mj_init_jpeg(self.ptr)
+
+    # -- reading / writing (host libjpeg) --
+    def read_jpeg_from_memory(self, data: bytes, max_pixel: int = 0) -> int:
+        return self.lib.mj_read_jpeg_from_memory(self.ptr, data, len(data), max_pixel)
+
+    def read_jpeg_from_file(self, path: str, max_pixel: int = 0) -> int:
+        return self.lib.mj_read_jpeg_from_file(self.ptr, path.encode(), max_pixel)
+
+    def write_jpeg_to_memory(self, options: int = 0) -> tuple[int, bytes]:
+        mem, n = C.c_void_p(), C.c_size_t()
+        rv = self.lib.mj_write_jpeg_to_memory(self.ptr, C.byref(mem), C.byref(n), options)
+        if rv != OK:
+            return rv, b""
+        out = C.string_at(mem, n.value)
+        _libc.free(mem)
+        return rv, out
+
+    def write_jpeg_to_file(self, path: str, options: int = 0) -> int:
+        return self.lib.mj_write_jpeg_to_file(self.ptr, path.encode(), options)
+
+    # -- the hot path --
+    def compose(self, dropon: "Dropon", align: int, offset_x: int = 0, offset_y: int = 0) -> int:
+        return self.lib.mj_compose(self.ptr, dropon.ptr if dropon is not None else None, align, offset_x, offset_y)
+
+    def effect_grayscale(self) -> int:
+        return self.lib.mj_effect_grayscale(self.ptr)
+
+    def effect_pixelate(self) -> int:
+        return self.lib.mj_effect_pixelate(self.ptr)
+
+    def effect_tint(self, cb_value: int, cr_value: int) -> int:
+        return self.lib.mj_effect_tint(self.ptr, cb_value, cr_value)
+
+    def effect_luminance(self, value: int) -> int:
+        return self.lib.mj_effect_luminance(self.ptr, value)
+
+    # -- plane access (mjx_host.h) --
+    def info(self) -> dict:
+        a = (C.c_int * 8)()
+        if self.lib.mjx_jpeg_image_info(self.ptr, a) != OK:
+            raise RuntimeError("no image loaded")
+        return dict(ncomp=a[0], colorspace=a[1], width=a[2], height=a[3], max_h=a[4], max_v=a[5])
+
+    def comp_info(self, c: int) -> dict:
+        a = (C.c_int * 8)()
+        if self.lib.mjx_jpeg_component_info(self.ptr, c, a) != OK:
+            raise RuntimeError("bad component")
+        return dict(wreal=a[0], hreal=a[1], h=a[2], v=a[3], wvirt=a[4], hvirt=a[5])
+
+    def sampling(self) -> list[tuple[int, int]]:
+        return [(self.comp_info(c)["h"], self.comp_info(c)["v"]) for c in range(self.info()["ncomp"])]
+
+    def layout(self) -> Layout:
+        L = Layout()
+        if self.lib.mjx_jpeg_layout(self.ptr, C.byref(L)) != OK:
+            raise RuntimeError("no image loaded")
+        return L
+
+    def qtable(self, c: int) -> np.ndarray:
+        q = np.zeros(64, np.uint16)
+        assert self.lib.mjx_jpeg_qtable(self.ptr, c, q.ctypes.data) == OK
+        return q
+
+    def plane(self, c: int) -> np.ndarray:
+        ci = self.comp_info(c)
+        a = np.zeros((ci["hvirt"], ci["wvirt"], 64), np.int16)
+        assert self.lib.mjx_jpeg_export_plane(self.ptr, c, a.ctypes.data) == OK
+        return a
+
+    def planes(self) -> list[np.ndarray]:
+        return [self.plane(c) for c in range(self.info()["ncomp"])]
+
+    def set_plane(self, c: int, a: np.ndarray) -> None:
+        a = np.ascontiguousarray(a, np.int16)
+        ci = self.comp_info(c)
+        assert a.shape == (ci["hvirt"], ci["wvirt"], 64)
+        assert self.lib.mjx_jpeg_import_plane(self.ptr, c, a.ctypes.data) == OK
+
+    def free(self) -> None:
+        if self.buf is not None:
+            self.lib.mj_free_jpeg(self.ptr)
+            self.buf = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Dropon:
+    """mj_dropon_t: an overlay and its alpha mask."""
+
+    def __init__(self):
+        self.lib = load_modjpeg()
+        self.struct = _DroponStruct()
+        self.ptr = C.cast(C.pointer(self.struct), C.c_void_p)
+        self.lib.mj_init_dropon(self.ptr)
+
+    def read_dropon_from_raw(self, raw: np.ndarray, colorspace: int, blend: int = 255) -> int:
+        raw = np.ascontiguousarray(raw, np.uint8)
+        h, w = raw.shape[:2]
+        return self.lib.mj_read_dropon_from_raw(self.ptr, raw.tobytes(), colorspace, w, h, blend)
+
+    def read_dropon_from_memory(self, data: bytes, mask: bytes | None = None, blend: int = 255) -> int:
+        return self.lib.mj_read_dropon_from_memory(self.ptr, data, len(data), mask, len(mask) if mask else 0, blend)
+
+    def read_dropon_from_file(self, path: str, mask_path: str | None = None, blend: int = 255) -> int:
+        return self.lib.mj_read_dropon_from_file(self.ptr, path.encode(), mask_path.encode() if mask_path else None, blend)
+
+    width = property(lambda self: self.struct.width)
+    height = property(lambda self: self.struct.height)
+    colorspace = property(lambda self: self.struct.colorspace)
+    blend = property(lambda self: self.struct.blend)
+
+    def image3(self) -> np.ndarray:
+        n = 3 * self.width * self.height
+        return np.ctypeslib.as_array(self.struct.image, (n,)).reshape(self.height, self.width, 3).copy()
+
+    def alpha3(self) -> np.ndarray:
+        n = 3 * self.width * self.height
+        return np.ctypeslib.as_array(self.struct.alpha, (n,)).reshape(self.height, self.width, 3).copy()
+
+    def free(self) -> None:
+        if self.struct is not None:
+            self.lib.mj_free_dropon(self.ptr)
+            self.struct = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -1,0 +1,34 @@
+/*
+ * mj_device.c -- the calling thread's engine context.  The reference has no global state and
+ * is re-entrant per object (SURVEY 8b "Threading"); to keep that, every host thread gets its
+ * own mjx_ctx (stream + staging pools), created on first use and destroyed with the thread.
+ * There is no CPU fallback: without a CUDA device the compute entry points fail loudly.
+ */
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "mj_private.h"
+
+static pthread_key_t  g_key;
+static pthread_once_t g_once = PTHREAD_ONCE_INIT;
+
+static void ctx_destructor(void *p) { mjx_ctx_destroy((mjx_ctx *)p); }
+static void make_key(void) { pthread_key_create(&g_key, ctx_destructor); }
+
+mjx_ctx *mjx_host_ctx(void) {
+    pthread_once(&g_once, make_key);
+    mjx_ctx *ctx = (mjx_ctx *)pthread_getspecific(g_key);
+    if(ctx != NULL) return ctx;
+    int         device = 0;
+    const char *env = getenv("MJX_DEVICE");
+    if(env != NULL && *env) device = atoi(env);
+    int rv = mjx_ctx_create(&ctx, device);
+    if(rv != MJX_OK || ctx == NULL) {
+        fprintf(stderr, "libmodjpeg (B200): no usable CUDA device %d (%d devices visible) - mj_compose/mj_effect_* need the GPU engine, there is no CPU fallback\n",
+                device, mjx_device_count());
+        return NULL;
+    }
+    pthread_setspecific(g_key, ctx);
+    return ctx;
+}

@@ -1,0 +1,200 @@
+// k1_dropon.cu -- K1, the dropon compile: crop/pad the overlay and its alpha mask onto an
+// MCU-aligned canvas, convert to the target JPEG's colour space, subsample with the target's
+// sampling factors, integer forward DCT, quality-100 quantisation -- one kernel, no libjpeg.
+// Replaces mj_compile_dropon (reference: src/dropon.c:325-576), i.e. the two libjpeg encodes
+// (src/image.c:257-347) and two coefficient decodes (src/dropon.c:430-576) it performs.
+//
+// The arithmetic is libjpeg-turbo 3.1.x's integer pipeline restated: jccolor.c
+// rgb_ycc_convert, jcsample.c fullsize/h2v1/h2v2/int_downsample, jfdctint.c jpeg_fdct_islow,
+// q == 1 quantisation -- bit-exact against the reference build (tests/test_k1_parity.py).
+//
+// Work unit = one output block of one component, 8 lanes, lane r = sample row r.  The padded
+// canvas of src/dropon.c:352-369 is never materialised: canvas pixels are fetched from the
+// dropon with crop / block offset applied on the fly and zero outside.
+// Output per component: D (overlay coefficients), W (alpha coefficients, DC += 1024,
+// src/dropon.c:542) and the per-block class word consumed by K2.
+// Roofline: HBM; algorithmic bytes = 6 B/px read (two 3-byte buffers) + 4 B per output coefficient.
+#include "mjx_device.cuh"
+
+namespace mjx {
+
+struct K1Comp {
+    int16_t  *D;
+    int16_t  *W;
+    uint32_t *meta;
+    int       wb, hb;
+    int       he, ve; // horizontal / vertical expansion = max_samp / samp
+    int       start;
+};
+
+struct K1Params {
+    K1Comp         comp[MJX_MAX_COMPONENTS];
+    int            ncomp, total_blocks;
+    const uint8_t *image3, *alpha3;
+    int            dw, dh;
+    int            dropon_cs, alpha_cs, target_cs;
+    int            boff_x, boff_y, crop_x, crop_y, crop_w, crop_h;
+    int            canvas_w, canvas_h;
+};
+
+// byte `ch` of canvas pixel (X, Y): the dropon inside the pasted crop, zero elsewhere
+__device__ __forceinline__ int canvas_byte(const K1Params &p, const uint8_t *src, int X, int Y, int ch) {
+    const int cx = X - p.boff_x, cy = Y - p.boff_y;
+    if(cx < 0 || cy < 0 || cx >= p.crop_w || cy >= p.crop_h) return 0;
+    return src[((size_t)(cy + p.crop_y) * p.dw + (cx + p.crop_x)) * 3 + ch];
+}
+
+// the sample libjpeg's colour converter produces for component c at canvas position (X, Y)
+__device__ __forceinline__ int canvas_sample(const K1Params &p, const uint8_t *src, int in_cs, int c, int X, int Y) {
+    if(in_cs == MJX_CS_GRAYSCALE) {
+        // reference: src/image.c:295-297,331 -- the 3-byte canvas is read as 1 byte per pixel
+        // with row stride = width, so sample (X, Y) is canvas byte Y*W + X.
+        const long long flat = (long long)Y * p.canvas_w + X;
+        const long long pix = flat / 3;
+        const int       ch = (int)(flat - pix * 3);
+        const int       pY = (int)(pix / p.canvas_w), pX = (int)(pix - (long long)pY * p.canvas_w);
+        return canvas_byte(p, src, pX, pY, ch);
+    }
+    const int cx = X - p.boff_x, cy = Y - p.boff_y;
+    int       p0 = 0, p1 = 0, p2 = 0;
+    if(cx >= 0 && cy >= 0 && cx < p.crop_w && cy < p.crop_h) {
+        const uint8_t *px = src + ((size_t)(cy + p.crop_y) * p.dw + (cx + p.crop_x)) * 3;
+        p0 = px[0], p1 = px[1], p2 = px[2];
+    }
+    if(in_cs == MJX_CS_RGB && p.target_cs != 2 /* JCS_RGB */)
+        return c == 0 ? rgb_to_y(p0, p1, p2) : c == 1 ? rgb_to_cb(p0, p1, p2) : rgb_to_cr(p0, p1, p2);
+    return c == 0 ? p0 : c == 1 ? p1 : p2;
+}
+
+// one row of 8 downsampled, level-shifted samples of block (bx, by)
+__device__ __forceinline__ void sample_row(const K1Params &p, const K1Comp &kc, const uint8_t *src, int in_cs, int c,
+                                           int bx, int by, int r, int *s) {
+    const int he = kc.he, ve = kc.ve, n = he * ve;
+#pragma unroll
+    for(int x = 0; x < 8; x++) {
+        const int X0 = (bx * 8 + x) * he, Y0 = (by * 8 + r) * ve;
+        int       sum = 0;
+        for(int j = 0; j < ve; j++)
+            for(int i = 0; i < he; i++) sum += canvas_sample(p, src, in_cs, c, X0 + i, Y0 + j);
+        // jcsample.c: h2v1 bias 0,1,0,1..; h2v2 bias 1,2,1,2..; otherwise round-half-up box mean
+        const int bias = (he == 2 && ve == 1) ? (x & 1) : (he == 2 && ve == 2) ? 1 + (x & 1) : n / 2;
+        s[x] = (sum + bias) / n - 128;
+    }
+}
+
+__device__ __forceinline__ void fdct_block(int (&s)[8], int r, unsigned mask) {
+    fdct8_islow<0>(s);
+    transpose8(s, r, mask);
+    fdct8_islow<1>(s);
+    transpose8(s, r, mask);
+#pragma unroll
+    for(int i = 0; i < 8; i++) s[i] = quant_q1(s[i]);
+}
+
+static constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads) k1_compile_kernel(const K1Params p) {
+    const int r = threadIdx.x & 7;
+    const int b = blockIdx.x * (kThreads / 8) + (threadIdx.x >> 3);
+    if(b >= p.total_blocks) return;
+    int c = 0;
+#pragma unroll
+    for(int i = 1; i < MJX_MAX_COMPONENTS; i++)
+        if(i < p.ncomp && b >= p.comp[i].start) c = i;
+    const K1Comp  &kc = p.comp[c];
+    const int      bi = b - kc.start;
+    const int      by = bi / kc.wb, bx = bi - by * kc.wb;
+    const unsigned mask = group_mask();
+
+    int s[8];
+    sample_row(p, kc, p.image3, p.dropon_cs, c, bx, by, r, s);
+    fdct_block(s, r, mask);
+    st_row(kc.D + (size_t)bi * 64 + r * 8, row_pack(s));
+
+    sample_row(p, kc, p.alpha3, p.alpha_cs, c, bx, by, r, s);
+    fdct_block(s, r, mask);
+    if(r == 0) s[0] += 1024; // reference: src/dropon.c:542
+    st_row(kc.W + (size_t)bi * 64 + r * 8, row_pack(s));
+    const uint32_t meta = classify_alpha(s, r, mask);
+    if(r == 0) kc.meta[bi] = meta;
+}
+
+// class words for a dropon whose D/W planes were uploaded from the host
+__global__ void __launch_bounds__(kThreads) classify_kernel(const int16_t *W, uint32_t *meta, int nblocks) {
+    const int r = threadIdx.x & 7;
+    const int b = blockIdx.x * (kThreads / 8) + (threadIdx.x >> 3);
+    if(b >= nblocks) return;
+    int w[8];
+    row_unpack(ld_row_keep(W + (size_t)b * 64 + r * 8), w);
+    const uint32_t m = classify_alpha(w, r, group_mask());
+    if(r == 0) meta[b] = m;
+}
+
+__global__ void count_classes_kernel(const uint32_t *meta, int nblocks, unsigned long long *counts) {
+    __shared__ unsigned int local[4];
+    if(threadIdx.x < 4) local[threadIdx.x] = 0;
+    __syncthreads();
+    for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < nblocks; i += gridDim.x * blockDim.x)
+        atomicAdd(&local[meta_cls(meta[i]) & 3u], 1u);
+    __syncthreads();
+    if(threadIdx.x < 4 && local[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)local[threadIdx.x]);
+}
+
+cudaError_t launch_k1(cudaStream_t s, const uint8_t *image3, const uint8_t *alpha3, int dw, int dh, int dropon_cs,
+                      int target_cs, int boff_x, int boff_y, int crop_x, int crop_y, int crop_w, int crop_h,
+                      int canvas_w, int canvas_h, int max_h, int max_v, mjx_dropon *d) {
+    K1Params p{};
+    p.ncomp = d->view.ncomp;
+    p.total_blocks = d->view.total_blocks;
+    for(int c = 0; c < p.ncomp; c++) {
+        p.comp[c].D = d->D[c];
+        p.comp[c].W = d->W[c];
+        p.comp[c].meta = d->meta[c];
+        p.comp[c].wb = d->view.comp[c].wb;
+        p.comp[c].hb = d->view.comp[c].hb;
+        p.comp[c].he = max_h / d->view.comp[c].hs;
+        p.comp[c].ve = max_v / d->view.comp[c].vs;
+        p.comp[c].start = d->view.comp[c].start;
+    }
+    p.image3 = image3;
+    p.alpha3 = alpha3;
+    p.dw = dw;
+    p.dh = dh;
+    p.dropon_cs = dropon_cs;
+    p.alpha_cs = target_cs == 2 ? MJX_CS_RGB : MJX_CS_YCC; // reference: src/dropon.c:411-414
+    p.target_cs = target_cs;
+    p.boff_x = boff_x, p.boff_y = boff_y;
+    p.crop_x = crop_x, p.crop_y = crop_y, p.crop_w = crop_w, p.crop_h = crop_h;
+    p.canvas_w = canvas_w, p.canvas_h = canvas_h;
+    if(p.total_blocks <= 0) return cudaSuccess;
+    const int per = kThreads / 8;
+    k1_compile_kernel<<<(p.total_blocks + per - 1) / per, kThreads, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_classify(cudaStream_t s, mjx_dropon *d) {
+    const int per = kThreads / 8;
+    for(int c = 0; c < d->view.ncomp; c++) {
+        const int nb = d->view.comp[c].wb * d->view.comp[c].hb;
+        if(nb <= 0) continue;
+        classify_kernel<<<(nb + per - 1) / per, kThreads, 0, s>>>(d->W[c], d->meta[c], nb);
+        cudaError_t e = cudaGetLastError();
+        if(e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t launch_count_classes(cudaStream_t s, const mjx_dropon *d, unsigned long long *counts_dev) {
+    for(int c = 0; c < d->view.ncomp; c++) {
+        const int nb = d->view.comp[c].wb * d->view.comp[c].hb;
+        if(nb <= 0) continue;
+        int grid = (nb + 255) / 256;
+        if(grid > 1024) grid = 1024;
+        count_classes_kernel<<<grid, 256, 0, s>>>(d->meta[c], nb, counts_dev);
+        cudaError_t e = cudaGetLastError();
+        if(e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+} // namespace mjx

@@ -1,0 +1,116 @@
+// k3_effects.cu -- K3, the coefficient-only effects, as one fused pass per component.
+// Replaces mj_effect_grayscale / _pixelate / _tint / _luminance (reference: src/effect.c:28-222).
+//
+// An effect pipeline is a short list of steps applied in order to every REAL block of a
+// component (width_in_blocks x height_in_blocks; MCU padding blocks are left alone, like the
+// reference's loops, src/effect.c:45-50):
+//   ZERO      all 64 coefficients := 0                                  (grayscale, per chroma plane)
+//   PIXELATE  coefficients 1..63 := 0                                   (pixelate)
+//   ADD_DC    DC = (int16)(DC*q0); DC = (int16)(DC+v); clamp +-2047; DC = (int16)(DC/q0)  (tint, luminance)
+// Because nothing ever un-zeroes an AC coefficient, a component whose list contains ZERO or
+// PIXELATE ends with all AC == 0 and only the DC needs to be read ("rewrite" kernel: 8 lanes per
+// block, 2 B read + 128 B written); a list of ADD_DC steps only touches the DC ("dc" kernel: one
+// thread per block, 2 B read + 2 B written; the DRAM sector floor is 32 B each way).
+// All integer, bit-exact including int16 wrap-around.  Roofline: HBM.
+#include "mjx_device.cuh"
+
+namespace mjx {
+
+static constexpr int kMaxOps = 16;
+
+struct K3Params {
+    const mjx_image_desc_t *items;
+    int                     comp;
+    int                     nops;   // steps that apply to `comp`, in order
+    int                     op[kMaxOps];
+    int                     value[kMaxOps];
+};
+
+// reference: src/effect.c:143-153 / 207-217
+__device__ __forceinline__ int add_dc(int dc, int q0, int value) {
+    int t = wrap16(dc * q0);
+    t = wrap16(t + value);
+    t = t > 2047 ? 2047 : (t < -2047 ? -2047 : t);
+    return wrap16(t / q0);
+}
+
+__device__ __forceinline__ int fold_dc(const K3Params &p, int dc, int q0) {
+    for(int i = 0; i < p.nops; i++) {
+        if(p.op[i] == MJX_FX_ZERO) dc = 0;
+        else if(p.op[i] == MJX_FX_ADD_DC) dc = add_dc(dc, q0, p.value[i]);
+    }
+    return dc;
+}
+
+static constexpr int kThreads = 256;
+
+// component ends with AC == 0: 8 lanes per block, every lane stores its (zero) row
+__global__ void __launch_bounds__(kThreads) k3_rewrite_kernel(const K3Params p, int first_is_zero) {
+    const mjx_image_desc_t &im = p.items[blockIdx.y];
+    const int c = p.comp, r = threadIdx.x & 7;
+    const int wreal = im.wreal[c], nblk = wreal * im.hreal[c], stride = im.stride_blocks[c];
+    const int q0 = im.q[c][0];
+    int16_t  *plane = reinterpret_cast<int16_t *>(im.plane[c]);
+    for(int bi = blockIdx.x * (kThreads / 8) + (threadIdx.x >> 3); bi < nblk; bi += gridDim.x * (kThreads / 8)) {
+        const int l = bi / wreal, k = bi - l * wreal;
+        int16_t  *bp = plane + ((size_t)l * stride + k) * 64;
+        Row8      row;
+        row.w[0] = row.w[1] = row.w[2] = row.w[3] = 0;
+        if(r == 0) {
+            int dc = first_is_zero ? 0 : (int)bp[0];
+            dc = fold_dc(p, dc, q0);
+            row.w[0] = (uint32_t)dc & 0xffffu;
+        }
+        st_row_stream(bp + r * 8, row);
+    }
+}
+
+// DC-only pipeline: one thread per block
+__global__ void __launch_bounds__(kThreads) k3_dc_kernel(const K3Params p) {
+    const mjx_image_desc_t &im = p.items[blockIdx.y];
+    const int c = p.comp;
+    const int wreal = im.wreal[c], nblk = wreal * im.hreal[c], stride = im.stride_blocks[c];
+    const int q0 = im.q[c][0];
+    int16_t  *plane = reinterpret_cast<int16_t *>(im.plane[c]);
+    for(int bi = blockIdx.x * kThreads + threadIdx.x; bi < nblk; bi += gridDim.x * kThreads) {
+        const int l = bi / wreal, k = bi - l * wreal;
+        int16_t  *bp = plane + ((size_t)l * stride + k) * 64;
+        bp[0] = (int16_t)fold_dc(p, (int)bp[0], q0);
+    }
+}
+
+cudaError_t launch_k3(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, int ncomp, const mjx_effect_op_t *ops,
+                      int nops, int *launches) {
+    if(n <= 0) return cudaSuccess;
+    for(int c = 0; c < ncomp; c++) {
+        K3Params p{};
+        p.items = items_dev;
+        p.comp = c;
+        bool rewrite = false;
+        for(int i = 0; i < nops; i++) {
+            if(ops[i].comp != c) continue;
+            if(p.nops == kMaxOps) return cudaErrorInvalidValue;
+            p.op[p.nops] = ops[i].op;
+            p.value[p.nops] = ops[i].value;
+            p.nops++;
+            if(ops[i].op == MJX_FX_ZERO || ops[i].op == MJX_FX_PIXELATE) rewrite = true;
+        }
+        if(p.nops == 0) continue;
+        // enough CTAs per image to fill 148 SMs a few times over; each CTA strides over its image
+        int gx = (148 * 16 + n - 1) / n;
+        if(gx < 1) gx = 1;
+        if(gx > 4096) gx = 4096;
+        for(int first = 0; first < n; first += 65535) {
+            const int cnt = n - first < 65535 ? n - first : 65535;
+            p.items = items_dev + first;
+            if(rewrite) k3_rewrite_kernel<<<dim3(gx, cnt), kThreads, 0, s>>>(p, p.op[0] == MJX_FX_ZERO ? 1 : 0);
+            else k3_dc_kernel<<<dim3(gx, cnt), kThreads, 0, s>>>(p);
+            cudaError_t e = cudaGetLastError();
+            if(e != cudaSuccess) return e;
+            if(launches) (*launches)++;
+        }
+    }
+    return cudaSuccess;
+}
+
+} // namespace mjx

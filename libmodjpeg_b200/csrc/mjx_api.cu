@@ -1,0 +1,653 @@
+// mjx_api.cu -- the extern "C" entry points of include/mjx.h: context and memory management,
+// the compiled-dropon object, and the host-pointer (staged) forms of K2 / K3.
+// No compute happens on the host here: the only host work is geometry (A1), argument checks and
+// gathering/scattering libjpeg rows into page-locked staging memory.
+#include <string.h>
+
+#include <new>
+
+#include "mjx_internal.cuh"
+#include "mjx_math.cuh"
+
+namespace mjx {
+
+int fail(mjx_ctx *ctx, cudaError_t e, const char *what) {
+    if(ctx) {
+        ctx->last_error = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    }
+    cudaGetLastError(); // clear the sticky-less error state
+    return e == cudaErrorMemoryAllocation ? MJX_ERR_MEMORY : MJX_ERR_DEVICE;
+}
+
+static int grow(mjx_ctx *ctx, void **p, size_t *have, size_t want, bool pinned) {
+    if(*have >= want) return MJX_OK;
+    size_t n = want + want / 4 + 4096;
+    MJX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for(int i = 0; i < mjx_ctx::kPipe; i++)
+        if(ctx->pipe[i]) MJX_CUDA(ctx, cudaStreamSynchronize(ctx->pipe[i]));
+    if(*p) {
+        if(pinned) cudaFreeHost(*p);
+        else cudaFree(*p);
+        *p = nullptr;
+        *have = 0;
+    }
+    if(pinned) MJX_CUDA(ctx, cudaHostAlloc(p, n, cudaHostAllocDefault));
+    else MJX_CUDA(ctx, cudaMalloc(p, n));
+    *have = n;
+    return MJX_OK;
+}
+
+int ensure_pin(mjx_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->pin, &ctx->pin_bytes, bytes, true); }
+int ensure_dev(mjx_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->dev, &ctx->dev_bytes, bytes, false); }
+int ensure_desc(mjx_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->desc_dev, &ctx->desc_bytes, bytes, false); }
+
+static int use_device(mjx_ctx *ctx) {
+    if(!ctx) return MJX_ERR_ARG;
+    MJX_CUDA(ctx, cudaSetDevice(ctx->device));
+    return MJX_OK;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+} // namespace mjx
+
+using namespace mjx;
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+
+int mjx_device_count(void) {
+    int         n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if(e != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int mjx_ctx_create(mjx_ctx **out, int device) {
+    if(!out) return MJX_ERR_ARG;
+    *out = nullptr;
+    if(device < 0 || device >= mjx_device_count()) return MJX_ERR_DEVICE;
+    mjx_ctx *ctx = new(std::nothrow) mjx_ctx();
+    if(!ctx) return MJX_ERR_MEMORY;
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if(e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if(e != cudaSuccess) {
+        cudaGetLastError();
+        delete ctx;
+        return MJX_ERR_DEVICE;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return MJX_OK;
+}
+
+void mjx_ctx_destroy(mjx_ctx *ctx) {
+    if(!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for(int i = 0; i < mjx_ctx::kPipe; i++) {
+        if(ctx->pipe[i]) {
+            cudaStreamSynchronize(ctx->pipe[i]);
+            cudaStreamDestroy(ctx->pipe[i]);
+        }
+        if(ctx->pipe_done[i]) cudaEventDestroy(ctx->pipe_done[i]);
+    }
+    if(ctx->pin) cudaFreeHost(ctx->pin);
+    if(ctx->dev) cudaFree(ctx->dev);
+    if(ctx->desc_dev) cudaFree(ctx->desc_dev);
+    if(ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int mjx_ctx_set_stream(mjx_ctx *ctx, void *cuda_stream) {
+    if(!ctx) return MJX_ERR_ARG;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return MJX_OK;
+}
+
+void *mjx_ctx_stream(mjx_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int mjx_ctx_sync(mjx_ctx *ctx) {
+    int rv = use_device(ctx);
+    if(rv) return rv;
+    MJX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MJX_OK;
+}
+
+const char *mjx_ctx_last_error(mjx_ctx *ctx) { return ctx ? ctx->last_error.c_str() : "no context"; }
+
+long long mjx_ctx_kernel_launches(mjx_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int mjx_device_alloc(mjx_ctx *ctx, void **ptr, size_t bytes) {
+    int rv = use_device(ctx);
+    if(rv) return rv;
+    if(!ptr) return MJX_ERR_ARG;
+    MJX_CUDA(ctx, cudaMalloc(ptr, bytes));
+    return MJX_OK;
+}
+
+void mjx_device_free(mjx_ctx *ctx, void *ptr) {
+    if(ctx && ptr && use_device(ctx) == MJX_OK) cudaFree(ptr);
+}
+
+int mjx_host_alloc(mjx_ctx *ctx, void **ptr, size_t bytes) {
+    int rv = use_device(ctx);
+    if(rv) return rv;
+    if(!ptr) return MJX_ERR_ARG;
+    MJX_CUDA(ctx, cudaHostAlloc(ptr, bytes, cudaHostAllocPortable));
+    return MJX_OK;
+}
+
+void mjx_host_free(mjx_ctx *ctx, void *ptr) {
+    if(ctx && ptr && use_device(ctx) == MJX_OK) cudaFreeHost(ptr);
+}
+
+int mjx_copy_h2d(mjx_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
+    int rv = use_device(ctx);
+    if(rv) return rv;
+    MJX_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return MJX_OK;
+}
+
+int mjx_copy_d2h(mjx_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
+    int rv = use_device(ctx);
+    if(rv) return rv;
+    MJX_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return MJX_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// A1: placement arithmetic (reference: src/compose.c:42-172).  Pure integer host code.
+// ---------------------------------------------------------------------------------------
+
+static void place_axis(int image_len, int dropon_len, int at_start, int at_end, int offset, int factor, int *crop_from,
+                       int *crop_len, int *blockoffset, int *block) {
+    // where the dropon's first pixel falls on the image along this axis
+    int pos = at_start ? 0 : (at_end ? image_len - dropon_len : image_len / 2 - dropon_len / 2);
+    pos += offset;
+    // part of the dropon that lies left of / above the image is cut away
+    int from = pos < 0 ? -pos : 0;
+    int len = dropon_len - from;
+    if(from > dropon_len || pos > image_len) len = 0;
+    else if(pos + from + len > image_len) len = image_len - from - pos;
+    *crop_from = from;
+    *crop_len = len;
+    // pixels between the MCU boundary and the dropon's first pixel (C remainder, clamped)
+    int bo = pos % factor;
+    *blockoffset = bo < 0 ? 0 : bo;
+    int b = pos / factor;
+    *block = b < 0 ? 0 : b;
+}
+
+void mjx_geometry(int image_width, int image_height, int h_factor, int v_factor, int dropon_width, int dropon_height,
+                  unsigned int align, int offset_x, int offset_y, mjx_geometry_t *g) {
+    if(!g) return;
+    memset(g, 0, sizeof(*g));
+    if(h_factor <= 0 || v_factor <= 0) return;
+    place_axis(image_width, dropon_width, (align & 1u) != 0, (align & 2u) != 0, offset_x, h_factor, &g->crop_x,
+               &g->crop_w, &g->blockoffset_x, &g->block_x);
+    place_axis(image_height, dropon_height, (align & 4u) != 0, (align & 8u) != 0, offset_y, v_factor, &g->crop_y,
+               &g->crop_h, &g->blockoffset_y, &g->block_y);
+    g->visible = (g->crop_w != 0 && g->crop_h != 0) ? 1 : 0;
+    if(!g->visible) g->blockoffset_x = g->blockoffset_y = g->block_x = g->block_y = 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// compiled dropon
+// ---------------------------------------------------------------------------------------
+
+static int layout_check(const mjx_layout_t *L, int *max_h, int *max_v) {
+    if(!L || L->ncomp < 1 || L->ncomp > MJX_MAX_COMPONENTS) return MJX_ERR_ARG;
+    int mh = 0, mv = 0, blocks = 0;
+    for(int c = 0; c < L->ncomp; c++) {
+        if(L->h_samp[c] < 1 || L->h_samp[c] > 4 || L->v_samp[c] < 1 || L->v_samp[c] > 4) return MJX_ERR_ARG;
+        if(L->h_samp[c] > mh) mh = L->h_samp[c];
+        if(L->v_samp[c] > mv) mv = L->v_samp[c];
+        blocks += L->h_samp[c] * L->v_samp[c];
+    }
+    for(int c = 0; c < L->ncomp; c++) // jcsample.c: only integral ratios are implemented
+        if(mh % L->h_samp[c] || mv % L->v_samp[c]) return MJX_ERR_UNSUPPORTED;
+    if(L->ncomp > 1 && blocks > 10) return MJX_ERR_UNSUPPORTED; // jcmaster.c: C_MAX_BLOCKS_IN_MCU
+    // component count implied by the colour space (jcparam.c jpeg_set_colorspace)
+    if(L->colorspace == 1 && L->ncomp != 1) return MJX_ERR_ARG;
+    if((L->colorspace == 2 || L->colorspace == 3) && L->ncomp != 3) return MJX_ERR_ARG;
+    if(L->colorspace < 1 || L->colorspace > 3) return MJX_ERR_UNSUPPORTED;
+    *max_h = mh;
+    *max_v = mv;
+    return MJX_OK;
+}
+
+// allocate the slab and fill the views for the given per-component block dims
+static int dropon_alloc(mjx_ctx *ctx, mjx_dropon **out, const mjx_layout_t *L, const int *wb, const int *hb) {
+    mjx_dropon *d = new(std::nothrow) mjx_dropon();
+    if(!d) return MJX_ERR_MEMORY;
+    d->device = ctx->device;
+    d->layout = *L;
+    size_t off = 0, offD[4], offW[4], offM[4];
+    int    start = 0;
+    for(int c = 0; c < L->ncomp; c++) {
+        size_t nb = (size_t)wb[c] * hb[c];
+        offD[c] = off;
+        off = align_up(off + nb * 128, 256);
+        offW[c] = off;
+        off = align_up(off + nb * 128, 256);
+        offM[c] = off;
+        off = align_up(off + nb * 4, 256);
+        d->view.comp[c].wb = wb[c];
+        d->view.comp[c].hb = hb[c];
+        d->view.comp[c].hs = L->h_samp[c];
+        d->view.comp[c].vs = L->v_samp[c];
+        d->view.comp[c].start = start;
+        start += (int)nb;
+    }
+    d->view.ncomp = L->ncomp;
+    d->view.total_blocks = start;
+    d->slab_bytes = off ? off : 256;
+    cudaError_t e = cudaMalloc(&d->slab, d->slab_bytes);
+    if(e != cudaSuccess) {
+        delete d;
+        return fail(ctx, e, "cudaMalloc(compiled dropon)");
+    }
+    for(int c = 0; c < L->ncomp; c++) {
+        d->D[c] = (int16_t *)((char *)d->slab + offD[c]);
+        d->W[c] = (int16_t *)((char *)d->slab + offW[c]);
+        d->meta[c] = (uint32_t *)((char *)d->slab + offM[c]);
+        d->view.comp[c].D = d->D[c];
+        d->view.comp[c].W = d->W[c];
+        d->view.comp[c].meta = d->meta[c];
+    }
+    *out = d;
+    return MJX_OK;
+}
+
+int mjx_dropon_compile(mjx_ctx *ctx, mjx_dropon **out, const uint8_t *image3, const uint8_t *alpha3, int width,
+                       int height, int dropon_colorspace, const mjx_layout_t *layout, int blockoffset_x,
+                       int blockoffset_y, int crop_x, int crop_y, int crop_w, int crop_h, int pixels_on_device) {
+    if(!out) return MJX_ERR_ARG;
+    *out = nullptr;
+    int rv = use_device(ctx);
+    if(rv) return rv;
+    if(!image3 || !alpha3 || width <= 0 || height <= 0) return MJX_ERR_ARG;
+    if(crop_w <= 0 || crop_h <= 0 || crop_x < 0 || crop_y < 0 || crop_x + crop_w > width || crop_y + crop_h > height ||
+       blockoffset_x < 0 || blockoffset_y < 0)
+        return MJX_ERR_ARG;
+    int max_h, max_v;
+    rv = layout_check(layout, &max_h, &max_v);
+    if(rv) return rv;
+    // conversions libjpeg's colour converter implements (jccolor.c jinit_color_converter);
+    // anything else makes the reference return MJ_ERR_ENCODE_JPEG (SURVEY 8b "Errors")
+    const int t = layout->colorspace;
+    const bool ok = (dropon_colorspace == MJX_CS_RGB) ||
+                    (dropon_colorspace == MJX_CS_YCC && (t == 3 || t == 1)) ||
+                    (dropon_colorspace == MJX_CS_GRAYSCALE && t == 1);
+    if(!ok) return MJX_ERR_UNSUPPORTED;
+
+    // canvas padded to whole MCUs (reference: src/dropon.c:340-350)
+    const int hf = max_h * 8, vf = max_v * 8;
+    int canvas_w = crop_w + blockoffset_x, canvas_h = crop_h + blockoffset_y;
+    if(canvas_w % hf) canvas_w += hf - canvas_w % hf;
+    if(canvas_h % vf) canvas_h += vf - canvas_h % vf;
+    int wb[4], hb[4];
+    for(int c = 0; c < layout->ncomp; c++) {
+        wb[c] = canvas_w / hf * layout->h_samp[c];
+        hb[c] = canvas_h / vf * layout->v_samp[c];
+    }
+    mjx_dropon *d = nullptr;
+    rv = dropon_alloc(ctx, &d, layout, wb, hb);
+    if(rv) return rv;
+
+    const uint8_t *img_dev = image3, *alp_dev = alpha3;
+    void          *tmp = nullptr;
+    const size_t   npx = (size_t)width * height * 3;
+    if(!pixels_on_device) {
+        cudaError_t e = cudaMalloc(&tmp, 2 * npx);
+        if(e == cudaSuccess) e = cudaMemcpyAsync(tmp, image3, npx, cudaMemcpyHostToDevice, ctx->stream);
+        if(e == cudaSuccess) e = cudaMemcpyAsync((char *)tmp + npx, alpha3, npx, cudaMemcpyHostToDevice, ctx->stream);
+        if(e != cudaSuccess) {
+            if(tmp) cudaFree(tmp);
+            mjx_dropon_free(d);
+            return fail(ctx, e, "upload dropon pixels");
+        }
+        img_dev = (const uint8_t *)tmp;
+        alp_dev = (const uint8_t *)tmp + npx;
+    }
+    cudaError_t e = launch_k1(ctx->stream, img_dev, alp_dev, width, height, dropon_colorspace, t, blockoffset_x,
+                              blockoffset_y, crop_x, crop_y, crop_w, crop_h, canvas_w, canvas_h, max_h, max_v, d);
+    ctx->launches++;
+    if(tmp) {
+        // the kernel reads tmp: free it only once the stream has drained
+        cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+        cudaFree(tmp);
+        if(e == cudaSuccess) e = e2;
+    }
+    if(e != cudaSuccess) {
+        mjx_dropon_free(d);
+        return fail(ctx, e, "k1_compile_kernel");
+    }
+    *out = d;
+    return MJX_OK;
+}
+
+int mjx_dropon_from_coefficients(mjx_ctx *ctx, mjx_dropon **out, const mjx_layout_t *layout, const int *wb,
+                                 const int *hb, const int16_t *const *D, const int16_t *const *W) {
+    if(!out) return MJX_ERR_ARG;
+    *out = nullptr;
+    int rv = use_device(ctx);
+    if(rv) return rv;
+    if(!layout || !wb || !hb || !D || !W) return MJX_ERR_ARG;
+    if(layout->ncomp < 1 || layout->ncomp > MJX_MAX_COMPONENTS) return MJX_ERR_ARG;
+    for(int c = 0; c < layout->ncomp; c++)
+        if(wb[c] < 0 || hb[c] < 0 || !D[c] || !W[c] || layout->h_samp[c] < 1 || layout->v_samp[c] < 1) return MJX_ERR_ARG;
+    mjx_dropon *d = nullptr;
+    rv = dropon_alloc(ctx, &d, layout, wb, hb);
+    if(rv) return rv;
+    cudaError_t e = cudaSuccess;
+    for(int c = 0; c < layout->ncomp && e == cudaSuccess; c++) {
+        size_t bytes = (size_t)wb[c] * hb[c] * 128;
+        if(!bytes) continue;
+        e = cudaMemcpyAsync(d->D[c], D[c], bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if(e == cudaSuccess) e = cudaMemcpyAsync(d->W[c], W[c], bytes, cudaMemcpyHostToDevice, ctx->stream);
+    }
+    if(e == cudaSuccess) {
+        e = launch_classify(ctx->stream, d);
+        ctx->launches += layout->ncomp;
+    }
+    if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); // host sources may go away after return
+    if(e != cudaSuccess) {
+        mjx_dropon_free(d);
+        return fail(ctx, e, "mjx_dropon_from_coefficients");
+    }
+    *out = d;
+    return MJX_OK;
+}
+
+void mjx_dropon_free(mjx_dropon *d) {
+    if(!d) return;
+    if(d->slab) {
+        cudaSetDevice(d->device);
+        cudaFree(d->slab);
+    }
+    delete d;
+}
+
+int mjx_dropon_ncomp(const mjx_dropon *d) { return d ? d->view.ncomp : 0; }
+
+int mjx_dropon_dims(const mjx_dropon *d, int comp, int *wb, int *hb) {
+    if(!d || comp < 0 || comp >= d->view.ncomp) return MJX_ERR_ARG;
+    if(wb) *wb = d->view.comp[comp].wb;
+    if(hb) *hb = d->view.comp[comp].hb;
+    return MJX_OK;
+}
+
+long long mjx_dropon_blocks(const mjx_dropon *d) { return d ? d->view.total_blocks : 0; }
+
+int mjx_dropon_download(mjx_ctx *ctx, const mjx_dropon *d, int comp, int16_t *D, int16_t *W, uint8_t *cls) {
+    int rv = use_device(ctx);
+    if(rv) return rv;
+    if(!d || comp < 0 || comp >= d->view.ncomp) return MJX_ERR_ARG;
+    const size_t nb = (size_t)d->view.comp[comp].wb * d->view.comp[comp].hb;
+    MJX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if(D) MJX_CUDA(ctx, cudaMemcpy(D, d->D[comp], nb * 128, cudaMemcpyDeviceToHost));
+    if(W) MJX_CUDA(ctx, cudaMemcpy(W, d->W[comp], nb * 128, cudaMemcpyDeviceToHost));
+    if(cls) {
+        std::vector<uint32_t> m(nb);
+        if(nb) MJX_CUDA(ctx, cudaMemcpy(m.data(), d->meta[comp], nb * 4, cudaMemcpyDeviceToHost));
+        for(size_t i = 0; i < nb; i++) cls[i] = (uint8_t)meta_cls(m[i]);
+    }
+    return MJX_OK;
+}
+
+int mjx_dropon_class_counts(mjx_ctx *ctx, const mjx_dropon *dc, long long counts[4]) {
+    int rv = use_device(ctx);
+    if(rv) return rv;
+    if(!dc || !counts) return MJX_ERR_ARG;
+    mjx_dropon *d = const_cast<mjx_dropon *>(dc);
+    std::lock_guard<std::mutex> lock(d->counts_mu);
+    if(!d->counts_valid) {
+        unsigned long long *dev = nullptr;
+        MJX_CUDA(ctx, cudaMalloc(&dev, 4 * sizeof(unsigned long long)));
+        cudaError_t e = cudaMemsetAsync(dev, 0, 4 * sizeof(unsigned long long), ctx->stream);
+        if(e == cudaSuccess) e = launch_count_classes(ctx->stream, d, dev);
+        ctx->launches += d->view.ncomp;
+        unsigned long long h[4] = {0, 0, 0, 0};
+        if(e == cudaSuccess) e = cudaMemcpyAsync(h, dev, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+        if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(dev);
+        if(e != cudaSuccess) return fail(ctx, e, "count classes");
+        for(int i = 0; i < 4; i++) d->counts[i] = (long long)h[i];
+        d->counts_valid = true;
+    }
+    for(int i = 0; i < 4; i++) counts[i] = d->counts[i];
+    return MJX_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// K2 entry points
+// ---------------------------------------------------------------------------------------
+
+int mjx_compose_batch_device(mjx_ctx *ctx, const mjx_image_desc_t *items_dev, int n, const mjx_dropon *d, int block_x,
+                             int block_y) {
+    int rv = use_device(ctx);
+    if(rv) return rv;
+    if(!items_dev || !d || n < 0 || block_x < 0 || block_y < 0) return MJX_ERR_ARG;
+    if(d->device != ctx->device) return MJX_ERR_ARG;
+    cudaError_t e = launch_k2(ctx->stream, items_dev, n, d->view, block_x, block_y);
+    ctx->launches += (n + 65534) / 65535;
+    if(e != cudaSuccess) return fail(ctx, e, "k2_compose_kernel");
+    return MJX_OK;
+}
+
+int mjx_compose_rows_host(mjx_ctx *ctx, int ncomp, int16_t *const *const *rows, const uint16_t *const *q,
+                          const mjx_dropon *d) {
+    int rv = use_device(ctx);
+    if(rv) return rv;
+    if(!rows || !q || !d || ncomp != d->view.ncomp || d->device != ctx->device) return MJX_ERR_ARG;
+    // staging layout: [desc][comp 0 ROI][comp 1 ROI]...
+    size_t off[MJX_MAX_COMPONENTS], total = align_up(sizeof(mjx_image_desc_t), 256);
+    for(int c = 0; c < ncomp; c++) {
+        if(!rows[c] || !q[c]) return MJX_ERR_ARG;
+        off[c] = total;
+        total = align_up(total + (size_t)d->view.comp[c].wb * d->view.comp[c].hb * 128, 256);
+    }
+    if((rv = ensure_pin(ctx, total)) || (rv = ensure_dev(ctx, total))) return rv;
+    char *pin = (char *)ctx->pin, *dev = (char *)ctx->dev;
+
+    mjx_image_desc_t *desc = (mjx_image_desc_t *)pin;
+    memset(desc, 0, sizeof(*desc));
+    for(int c = 0; c < ncomp; c++) {
+        const int wb = d->view.comp[c].wb, hb = d->view.comp[c].hb;
+        desc->plane[c] = (uint64_t)(uintptr_t)(dev + off[c]);
+        desc->stride_blocks[c] = wb;
+        desc->rows[c] = hb;
+        desc->wreal[c] = wb;
+        desc->hreal[c] = hb;
+        memcpy(desc->q[c], q[c], 128);
+        for(int l = 0; l < hb; l++) {
+            if(!rows[c][l]) return MJX_ERR_ARG;
+            memcpy(pin + off[c] + (size_t)l * wb * 128, rows[c][l], (size_t)wb * 128);
+        }
+    }
+    MJX_CUDA(ctx, cudaMemcpyAsync(dev, pin, total, cudaMemcpyHostToDevice, ctx->stream));
+    // the staged region starts at the dropon's origin: MCU position (0, 0)
+    cudaError_t e = launch_k2(ctx->stream, (const mjx_image_desc_t *)dev, 1, d->view, 0, 0);
+    ctx->launches++;
+    if(e != cudaSuccess) return fail(ctx, e, "k2_compose_kernel");
+    const size_t head = align_up(sizeof(mjx_image_desc_t), 256);
+    MJX_CUDA(ctx, cudaMemcpyAsync(pin + head, dev + head, total - head, cudaMemcpyDeviceToHost, ctx->stream));
+    MJX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for(int c = 0; c < ncomp; c++) {
+        const int wb = d->view.comp[c].wb, hb = d->view.comp[c].hb;
+        for(int l = 0; l < hb; l++) memcpy(rows[c][l], pin + off[c] + (size_t)l * wb * 128, (size_t)wb * 128);
+    }
+    return MJX_OK;
+}
+
+static int pipe_init(mjx_ctx *ctx) {
+    for(int i = 0; i < mjx_ctx::kPipe; i++) {
+        if(!ctx->pipe[i]) MJX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->pipe[i], cudaStreamNonBlocking));
+        if(!ctx->pipe_done[i]) MJX_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_done[i], cudaEventDisableTiming));
+    }
+    return MJX_OK;
+}
+
+int mjx_compose_batch_host(mjx_ctx *ctx, const mjx_host_image_t *items, int n, const mjx_dropon *d, int block_x,
+                           int block_y) {
+    int rv = use_device(ctx);
+    if(rv) return rv;
+    if(!items || !d || n < 0 || block_x < 0 || block_y < 0 || d->device != ctx->device) return MJX_ERR_ARG;
+    if(n == 0) return MJX_OK;
+    const int ncomp = d->view.ncomp;
+    // validate that the dropon's region lies inside every plane
+    for(int i = 0; i < n; i++)
+        for(int c = 0; c < ncomp; c++) {
+            const DropComp &dc = d->view.comp[c];
+            if(!items[i].plane[c] || !items[i].q[c]) return MJX_ERR_ARG;
+            if(block_x * dc.hs + dc.wb > items[i].stride_blocks[c] || block_y * dc.vs + dc.hb > items[i].rows[c])
+                return MJX_ERR_ARG;
+        }
+    // per pipeline slot: one image's region in device memory; descriptors for all images in pinned memory
+    size_t off[MJX_MAX_COMPONENTS], slot = 0;
+    for(int c = 0; c < ncomp; c++) {
+        off[c] = slot;
+        slot = align_up(slot + (size_t)d->view.comp[c].wb * d->view.comp[c].hb * 128, 256);
+    }
+    const int    P = mjx_ctx::kPipe;
+    const size_t desc_sz = align_up(sizeof(mjx_image_desc_t), 256);
+    if((rv = pipe_init(ctx)) || (rv = ensure_dev(ctx, slot * P)) || (rv = ensure_desc(ctx, desc_sz * P)) ||
+       (rv = ensure_pin(ctx, desc_sz * (size_t)n)))
+        return rv;
+    char *dev = (char *)ctx->dev, *pin = (char *)ctx->pin, *ddev = (char *)ctx->desc_dev;
+
+    // the pipeline streams start after whatever is queued on the ctx stream
+    cudaEvent_t start;
+    MJX_CUDA(ctx, cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+    MJX_CUDA(ctx, cudaEventRecord(start, ctx->stream));
+    for(int s = 0; s < P; s++) MJX_CUDA(ctx, cudaStreamWaitEvent(ctx->pipe[s], start, 0));
+    cudaEventDestroy(start);
+
+    for(int i = 0; i < n; i++) {
+        const int         s = i % P;
+        cudaStream_t      st = ctx->pipe[s];
+        char             *base = dev + slot * s;
+        mjx_image_desc_t *desc = (mjx_image_desc_t *)(pin + desc_sz * i);
+        memset(desc, 0, sizeof(*desc));
+        for(int c = 0; c < ncomp; c++) {
+            const DropComp &dc = d->view.comp[c];
+            desc->plane[c] = (uint64_t)(uintptr_t)(base + off[c]);
+            desc->stride_blocks[c] = dc.wb;
+            desc->rows[c] = dc.hb;
+            desc->wreal[c] = dc.wb;
+            desc->hreal[c] = dc.hb;
+            memcpy(desc->q[c], items[i].q[c], 128);
+        }
+        MJX_CUDA(ctx, cudaMemcpyAsync(ddev + desc_sz * s, desc, sizeof(*desc), cudaMemcpyHostToDevice, st));
+        for(int c = 0; c < ncomp; c++) {
+            const DropComp &dc = d->view.comp[c];
+            const size_t    sp = (size_t)items[i].stride_blocks[c] * 128, wbytes = (size_t)dc.wb * 128;
+            const char     *src = (const char *)items[i].plane[c] + ((size_t)block_y * dc.vs * items[i].stride_blocks[c] + (size_t)block_x * dc.hs) * 128;
+            if(sp == wbytes) MJX_CUDA(ctx, cudaMemcpyAsync(base + off[c], src, wbytes * dc.hb, cudaMemcpyHostToDevice, st));
+            else MJX_CUDA(ctx, cudaMemcpy2DAsync(base + off[c], wbytes, src, sp, wbytes, dc.hb, cudaMemcpyHostToDevice, st));
+        }
+        cudaError_t e = launch_k2(st, (const mjx_image_desc_t *)(ddev + desc_sz * s), 1, d->view, 0, 0);
+        ctx->launches++;
+        if(e != cudaSuccess) return fail(ctx, e, "k2_compose_kernel");
+        for(int c = 0; c < ncomp; c++) {
+            const DropComp &dc = d->view.comp[c];
+            const size_t    sp = (size_t)items[i].stride_blocks[c] * 128, wbytes = (size_t)dc.wb * 128;
+            char           *dst = (char *)items[i].plane[c] + ((size_t)block_y * dc.vs * items[i].stride_blocks[c] + (size_t)block_x * dc.hs) * 128;
+            if(sp == wbytes) MJX_CUDA(ctx, cudaMemcpyAsync(dst, base + off[c], wbytes * dc.hb, cudaMemcpyDeviceToHost, st));
+            else MJX_CUDA(ctx, cudaMemcpy2DAsync(dst, sp, base + off[c], wbytes, wbytes, dc.hb, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for(int s = 0; s < P; s++) MJX_CUDA(ctx, cudaStreamSynchronize(ctx->pipe[s]));
+    return MJX_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// K3 entry points
+// ---------------------------------------------------------------------------------------
+
+static int ops_check(int ncomp, const mjx_effect_op_t *ops, int nops) {
+    if(nops < 0 || (nops > 0 && !ops)) return MJX_ERR_ARG;
+    for(int i = 0; i < nops; i++) {
+        if(ops[i].comp < 0 || ops[i].comp >= ncomp) return MJX_ERR_ARG;
+        if(ops[i].op != MJX_FX_ZERO && ops[i].op != MJX_FX_PIXELATE && ops[i].op != MJX_FX_ADD_DC) return MJX_ERR_ARG;
+    }
+    return MJX_OK;
+}
+
+int mjx_effects_batch_device(mjx_ctx *ctx, const mjx_image_desc_t *items_dev, int n, int ncomp,
+                             const mjx_effect_op_t *ops, int nops) {
+    int rv = use_device(ctx);
+    if(rv) return rv;
+    if(!items_dev || n < 0 || ncomp < 1 || ncomp > MJX_MAX_COMPONENTS) return MJX_ERR_ARG;
+    if((rv = ops_check(ncomp, ops, nops))) return rv;
+    int         launches = 0;
+    cudaError_t e = launch_k3(ctx->stream, items_dev, n, ncomp, ops, nops, &launches);
+    ctx->launches += launches;
+    if(e != cudaSuccess) return fail(ctx, e, "k3 effects kernel");
+    return MJX_OK;
+}
+
+int mjx_effects_rows_host(mjx_ctx *ctx, int ncomp, int16_t *const *const *rows, const int *wreal, const int *hreal,
+                          const uint16_t *const *q, const mjx_effect_op_t *ops, int nops) {
+    int rv = use_device(ctx);
+    if(rv) return rv;
+    if(!rows || !wreal || !hreal || !q || ncomp < 1 || ncomp > MJX_MAX_COMPONENTS) return MJX_ERR_ARG;
+    if((rv = ops_check(ncomp, ops, nops))) return rv;
+    bool   used[MJX_MAX_COMPONENTS] = {}, need_read[MJX_MAX_COMPONENTS] = {};
+    for(int i = 0; i < nops; i++) {
+        const int c = ops[i].comp;
+        if(!used[c]) need_read[c] = ops[i].op != MJX_FX_ZERO; // a leading ZERO makes the old content irrelevant
+        used[c] = true;
+    }
+    size_t off[MJX_MAX_COMPONENTS], total = align_up(sizeof(mjx_image_desc_t), 256);
+    for(int c = 0; c < ncomp; c++) {
+        if(!used[c]) continue;
+        if(!rows[c] || !q[c] || wreal[c] < 0 || hreal[c] < 0) return MJX_ERR_ARG;
+        off[c] = total;
+        total = align_up(total + (size_t)wreal[c] * hreal[c] * 128, 256);
+    }
+    if((rv = ensure_pin(ctx, total)) || (rv = ensure_dev(ctx, total))) return rv;
+    char             *pin = (char *)ctx->pin, *dev = (char *)ctx->dev;
+    mjx_image_desc_t *desc = (mjx_image_desc_t *)pin;
+    memset(desc, 0, sizeof(*desc));
+    const size_t head = align_up(sizeof(mjx_image_desc_t), 256);
+    for(int c = 0; c < ncomp; c++) {
+        if(!used[c]) continue;
+        desc->plane[c] = (uint64_t)(uintptr_t)(dev + off[c]);
+        desc->stride_blocks[c] = wreal[c];
+        desc->rows[c] = hreal[c];
+        desc->wreal[c] = wreal[c];
+        desc->hreal[c] = hreal[c];
+        memcpy(desc->q[c], q[c], 128);
+        if(need_read[c])
+            for(int l = 0; l < hreal[c]; l++) memcpy(pin + off[c] + (size_t)l * wreal[c] * 128, rows[c][l], (size_t)wreal[c] * 128);
+    }
+    MJX_CUDA(ctx, cudaMemcpyAsync(dev, pin, head, cudaMemcpyHostToDevice, ctx->stream));
+    for(int c = 0; c < ncomp; c++)
+        if(used[c] && need_read[c])
+            MJX_CUDA(ctx, cudaMemcpyAsync(dev + off[c], pin + off[c], (size_t)wreal[c] * hreal[c] * 128, cudaMemcpyHostToDevice, ctx->stream));
+    int         launches = 0;
+    cudaError_t e = launch_k3(ctx->stream, (const mjx_image_desc_t *)dev, 1, ncomp, ops, nops, &launches);
+    ctx->launches += launches;
+    if(e != cudaSuccess) return fail(ctx, e, "k3 effects kernel");
+    for(int c = 0; c < ncomp; c++)
+        if(used[c])
+            MJX_CUDA(ctx, cudaMemcpyAsync(pin + off[c], dev + off[c], (size_t)wreal[c] * hreal[c] * 128, cudaMemcpyDeviceToHost, ctx->stream));
+    MJX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for(int c = 0; c < ncomp; c++)
+        if(used[c])
+            for(int l = 0; l < hreal[c]; l++) memcpy(rows[c][l], pin + off[c] + (size_t)l * wreal[c] * 128, (size_t)wreal[c] * 128);
+    return MJX_OK;
+}
+
+} // extern "C"

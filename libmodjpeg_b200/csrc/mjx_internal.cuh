@@ -1,0 +1,95 @@
+// mjx_internal.cuh -- host-side objects behind the opaque handles of include/mjx.h and the
+// parameter blocks handed to the kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "mjx.h"
+
+namespace mjx {
+
+// ---- device-side view of one component of a compiled dropon -----------------------------
+struct DropComp {
+    const int16_t  *D;    // [hb][wb][64] overlay coefficients (libjpeg q=1 integer DCT)
+    const int16_t  *W;    // [hb][wb][64] alpha coefficients, DC += 1024
+    const uint32_t *meta; // [hb][wb]     class | (alpha DC << 8)
+    int wb, hb;           // blocks
+    int hs, vs;           // sampling factors of this component in the target image
+    int start;            // index of this component's first block in the flattened block list
+};
+
+struct DropView {
+    DropComp comp[MJX_MAX_COMPONENTS];
+    int      ncomp;
+    int      total_blocks;
+};
+
+} // namespace mjx
+
+// ---- opaque handles -------------------------------------------------------------------
+struct mjx_dropon {
+    int            device = 0;
+    mjx_layout_t   layout{};
+    void          *slab = nullptr; // one allocation holding every plane below
+    size_t         slab_bytes = 0;
+    mjx::DropView  view{};
+    int16_t       *D[MJX_MAX_COMPONENTS] = {};
+    int16_t       *W[MJX_MAX_COMPONENTS] = {};
+    uint32_t      *meta[MJX_MAX_COMPONENTS] = {};
+    std::mutex     counts_mu;
+    bool           counts_valid = false;
+    long long      counts[4] = {};
+};
+
+struct mjx_ctx {
+    int          device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr; // own_stream or a borrowed one
+    std::string  last_error;
+    long long    launches = 0;
+    int          sm_count = 0;
+
+    // staging pools for the host-pointer entry points (grown on demand, reused across calls)
+    void  *pin = nullptr;
+    size_t pin_bytes = 0;
+    void  *dev = nullptr;
+    size_t dev_bytes = 0;
+    void  *desc_dev = nullptr; // device array of mjx_image_desc_t for staged launches
+    size_t desc_bytes = 0;
+
+    // extra streams + events for the pipelined batch-host path
+    static const int kPipe = 3;
+    cudaStream_t pipe[kPipe] = {};
+    cudaEvent_t  pipe_done[kPipe] = {};
+};
+
+namespace mjx {
+
+int  fail(mjx_ctx *ctx, cudaError_t e, const char *what);
+int  ensure_pin(mjx_ctx *ctx, size_t bytes);
+int  ensure_dev(mjx_ctx *ctx, size_t bytes);
+int  ensure_desc(mjx_ctx *ctx, size_t bytes);
+
+// kernel launchers (each returns a cudaError_t from the launch)
+cudaError_t launch_k1(cudaStream_t s, const uint8_t *image3, const uint8_t *alpha3, int dw, int dh, int dropon_cs,
+                      int target_cs, int boff_x, int boff_y, int crop_x, int crop_y, int crop_w, int crop_h,
+                      int canvas_w, int canvas_h, int max_h, int max_v, mjx_dropon *d);
+cudaError_t launch_classify(cudaStream_t s, mjx_dropon *d);
+cudaError_t launch_k2(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, const DropView &view, int block_x,
+                      int block_y);
+cudaError_t launch_k3(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, int ncomp, const mjx_effect_op_t *ops,
+                      int nops, int *launches);
+cudaError_t launch_count_classes(cudaStream_t s, const mjx_dropon *d, unsigned long long *counts_dev);
+
+} // namespace mjx
+
+#define MJX_CUDA(ctx, call)                                        \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if(e__ != cudaSuccess) return mjx::fail(ctx, e__, #call);  \
+    } while(0)

