@@ -221,7 +221,10 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
         dist.init_process_group("nccl", device_id=dev)
 
     engine = M.Engine(local_rank)
-    stream = torch.cuda.current_stream(dev)
+    # torch is plumbing here: it owns the device memory and the stream the kernels are launched
+    # on, so that torch.cuda.Event brackets exactly the engine's launches
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     engine.set_stream(stream.cuda_stream)
 
     # ---- inputs -------------------------------------------------------------------------

@@ -100,7 +100,8 @@ typedef struct {
 int         mjx_device_count(void);
 int         mjx_ctx_create(mjx_ctx **ctx, int device);
 void        mjx_ctx_destroy(mjx_ctx *ctx);
-int         mjx_ctx_set_stream(mjx_ctx *ctx, void *cuda_stream); /* borrow a caller-owned cudaStream_t (NULL: back to the ctx's own) */
+int         mjx_ctx_set_stream(mjx_ctx *ctx, void *cuda_stream); /* borrow a caller-owned cudaStream_t; the handle is used as is (0 = the legacy default stream) */
+int         mjx_ctx_use_own_stream(mjx_ctx *ctx);                /* back to the stream the ctx created */
 void       *mjx_ctx_stream(mjx_ctx *ctx);
 int         mjx_ctx_sync(mjx_ctx *ctx);
 const char *mjx_ctx_last_error(mjx_ctx *ctx);

@@ -95,6 +95,7 @@ def load_mjx() -> C.CDLL:
     L.mjx_ctx_destroy.argtypes = [vp]
     L.mjx_ctx_destroy.restype = None
     L.mjx_ctx_set_stream.argtypes = [vp, vp]
+    L.mjx_ctx_use_own_stream.argtypes = [vp]
     L.mjx_ctx_stream.argtypes = [vp]
     L.mjx_ctx_stream.restype = vp
     L.mjx_ctx_sync.argtypes = [vp]
@@ -216,7 +217,11 @@ class Engine:
 
     # ---- context ----------------------------------------------------------------------
     def set_stream(self, cuda_stream: int | None) -> None:
-        self._check(self.lib.mjx_ctx_set_stream(self.ctx, C.c_void_p(cuda_stream or 0)), "mjx_ctx_set_stream")
+        """Run on a caller-owned cudaStream_t (e.g. torch's); None goes back to the ctx's own stream."""
+        if cuda_stream is None:
+            self._check(self.lib.mjx_ctx_use_own_stream(self.ctx), "mjx_ctx_use_own_stream")
+        else:
+            self._check(self.lib.mjx_ctx_set_stream(self.ctx, C.c_void_p(cuda_stream)), "mjx_ctx_set_stream")
 
     @property
     def stream(self) -> int:

@@ -109,7 +109,13 @@ void mjx_ctx_destroy(mjx_ctx *ctx) {
 
 int mjx_ctx_set_stream(mjx_ctx *ctx, void *cuda_stream) {
     if(!ctx) return MJX_ERR_ARG;
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return MJX_OK;
+}
+
+int mjx_ctx_use_own_stream(mjx_ctx *ctx) {
+    if(!ctx) return MJX_ERR_ARG;
+    ctx->stream = ctx->own_stream;
     return MJX_OK;
 }
 
