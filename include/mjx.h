@@ -102,6 +102,9 @@ int         mjx_ctx_create(mjx_ctx **ctx, int device);
 void        mjx_ctx_destroy(mjx_ctx *ctx);
 int         mjx_ctx_set_stream(mjx_ctx *ctx, void *cuda_stream); /* borrow a caller-owned cudaStream_t; the handle is used as is (0 = the legacy default stream) */
 int         mjx_ctx_use_own_stream(mjx_ctx *ctx);                /* back to the stream the ctx created */
+/* strict = 1: K2 runs as one kernel that reproduces the reference's int16 wrap-around on out-of-range
+ * products (adversarial streams); default 0: the fast kernels, identical on every encoder-produced JPEG */
+int         mjx_ctx_set_strict(mjx_ctx *ctx, int strict);
 void       *mjx_ctx_stream(mjx_ctx *ctx);
 int         mjx_ctx_sync(mjx_ctx *ctx);
 const char *mjx_ctx_last_error(mjx_ctx *ctx);

@@ -96,6 +96,7 @@ def load_mjx() -> C.CDLL:
     L.mjx_ctx_destroy.restype = None
     L.mjx_ctx_set_stream.argtypes = [vp, vp]
     L.mjx_ctx_use_own_stream.argtypes = [vp]
+    L.mjx_ctx_set_strict.argtypes = [vp, C.c_int]
     L.mjx_ctx_stream.argtypes = [vp]
     L.mjx_ctx_stream.restype = vp
     L.mjx_ctx_sync.argtypes = [vp]
@@ -222,6 +223,10 @@ class Engine:
             self._check(self.lib.mjx_ctx_use_own_stream(self.ctx), "mjx_ctx_use_own_stream")
         else:
             self._check(self.lib.mjx_ctx_set_stream(self.ctx, C.c_void_p(cuda_stream)), "mjx_ctx_set_stream")
+
+    def set_strict(self, strict: bool) -> None:
+        """strict: one K2 kernel with the reference's int16 wrap-around (adversarial inputs); default fast kernels"""
+        self._check(self.lib.mjx_ctx_set_strict(self.ctx, 1 if strict else 0), "mjx_ctx_set_strict")
 
     @property
     def stream(self) -> int:

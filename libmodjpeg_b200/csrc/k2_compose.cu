@@ -2,21 +2,46 @@
 // to the image's own tables.  Replaces mj_compose_with_mask + mj_convolve
 // (reference: src/compose.c:237-342, src/convolve.c:29-1099).
 //
-// Work unit = one 8x8 block of one component of one image, owned by 8 lanes (lane r = row r,
-// one 128-bit load/store per plane).  The block's class, written by K1, decides what is touched:
-//   T       nothing: the image block is neither loaded nor stored
-//   OPAQUE  load D, store trunc(D / q)                      (bit-exact)
-//   U       load I and D, one fp32 multiply per coefficient (bit-exact, see mjx_math.cuh)
-//   G       load I, D, W; pixel-domain blend: alpha = IDCT(W)/255, Y = DCT(alpha * IDCT(D - I*q))
-//           -- the closed form of the reference's 64 sparse DCT-domain products,
-//           within +-1 quantisation step of it.
-// Roofline: HBM.  Algorithmic bytes per block: T 0, OPAQUE 128, U/G 256 of image traffic, plus
-// the compiled dropon once per launch (L2-resident across the images of a batch).
+// The class K1 gave every dropon block decides what is touched:
+//   T       nothing: never listed, never loaded, never stored
+//   OPAQUE  store trunc(D / q); the image block is not read                       (bit-exact)
+//   U       one fp32 multiply per coefficient on the dequantised difference        (bit-exact)
+//   G       pixel-domain blend  Y = DCT2(A * IDCT2(D - I*q)),  A = IDCT2(W)/255 precomputed by K1:
+//           the closed form of the reference's 64 sparse DCT-domain products, within +-1
+//           quantisation step of it.
+//
+// Three kernels per call (one launch each, any number of images):
+//   k2_tables_kernel   per (image, component): q as float, q * IDCT prescale, biased 1/q
+//   k2_simple_kernel   OPAQUE/U list; 8 lanes per block (lane r = row r, one 128-bit access per
+//                      plane), D row kept in registers while the lanes walk the images
+//   k2_generic_kernel  G list; one thread owns one block (all 64 coefficients in registers, so
+//                      the 2-D transforms need no shuffles), one warp owns a tile of 32 list
+//                      entries whose A and Ds stay in shared memory while the warp streams the
+//                      images through: cp.async double buffering of the 32 image blocks (4 KB) of
+//                      the next image, XOR-swizzled so that the thread-per-block 128-bit shared
+//                      loads are bank-conflict free; results go back through the same buffer so
+//                      global stores are coalesced.  Work (tile x image chunk) is claimed from an
+//                      atomic counter by persistent warps, one 6-warp CTA per SM.
+//   The arithmetic stays in the fp32 pipe: on sm_100a F2I/FRND issue at 1/8 rate and I2F.S16/SHFL
+//   at 1/4 (profiles/microbench/ubench.txt), so truncation and int16 packing use magic-number adds.
+//
+// k2_strict_kernel is the first-generation single kernel (8 lanes per block, warp-shuffle
+// transposes, integer requantisation).  It reproduces the reference's int16 wrap-around on
+// out-of-range products exactly and is selected with mjx_ctx_set_strict(); the fast kernels equal
+// it whenever |I*q| and the blended value stay inside int16, i.e. for every JPEG a conforming
+// encoder writes.
+//
+// Roofline: HBM.  Algorithmic bytes per block: T 0, OPAQUE 128 (write), U/G 256 (read + write),
+// plus the compiled dropon once per launch (L2 / shared-memory resident across the images).
 #include "mjx_device.cuh"
 
 namespace mjx {
 
-struct K2Params {
+// =========================================================================================
+// strict kernel (all classes, exact int16 wrap-around)
+// =========================================================================================
+
+struct StrictParams {
     DropView                drop;
     const mjx_image_desc_t *items;
     int                     block_x, block_y; // dropon origin on the image, in MCUs
@@ -25,7 +50,7 @@ struct K2Params {
 static constexpr int kThreads = 256;
 static constexpr int kBlocksPerCta = kThreads / 8;
 
-__global__ void __launch_bounds__(kThreads) k2_compose_kernel(const K2Params p) {
+__global__ void __launch_bounds__(kThreads) k2_strict_kernel(const StrictParams p) {
     const int r = threadIdx.x & 7;
     const int b = blockIdx.x * kBlocksPerCta + (threadIdx.x >> 3);
     if(b >= p.drop.total_blocks) return;
@@ -49,7 +74,7 @@ __global__ void __launch_bounds__(kThreads) k2_compose_kernel(const K2Params p) 
     int16_t       *ip = reinterpret_cast<int16_t *>(im.plane[c]) + ((size_t)row * im.stride_blocks[c] + col) * 64 + r * 8;
     const int16_t *dp = dc.D + (size_t)bi * 64 + r * 8;
 
-    int q[8], D[8], out[8];
+    int   q[8], D[8], out[8];
     float rq[8];
     {
         Row8 qr = ld_row_keep(&im.q[c][r * 8]);
@@ -79,12 +104,11 @@ __global__ void __launch_bounds__(kThreads) k2_compose_kernel(const K2Params p) 
         return;
     }
 
-    // ---- generic block -------------------------------------------------------------------
     const unsigned mask = group_mask();
-    int W[8], deq[8];
+    int            W[8], deq[8];
     row_unpack(ld_row_keep(dc.W + (size_t)bi * 64 + r * 8), W);
 
-    float x[8], a[8];
+    float       x[8], a[8];
     const float pr = c_inv_scale[r];
     {
         const float isc[8] = MJX_INV_SCALE_INIT;
@@ -119,20 +143,336 @@ __global__ void __launch_bounds__(kThreads) k2_compose_kernel(const K2Params p) 
     st_row_stream(ip, row_pack(out));
 }
 
+// =========================================================================================
+// fast path, kernel 1: float tables per (image, component)
+// =========================================================================================
+
+__global__ void __launch_bounds__(64) k2_tables_kernel(const mjx_image_desc_t *items, int ncomp, float *tables) {
+    const int i = threadIdx.x, c = blockIdx.y;
+    if(c >= ncomp) return;
+    const int   q = items[blockIdx.x].q[c][i];
+    const float s = c_inv_scale[i >> 3] * c_inv_scale[i & 7];
+    float      *t = tables + ((size_t)blockIdx.x * ncomp + c) * kTabFloats;
+    t[kTabQf + i] = (float)q;
+    t[kTabQs + i] = (float)q * s;
+    t[kTabRq + i] = quant_rcp(q > 0 ? q : 1);
+}
+
+// =========================================================================================
+// fast path, kernel 2: OPAQUE and U blocks
+// =========================================================================================
+
+struct FastParams {
+    DropView                drop;
+    const mjx_image_desc_t *items;
+    const float            *tables;
+    unsigned int           *counter; // work-stealing counter of the generic kernel
+    int                     n;       // images
+    int                     block_x, block_y;
+    int                     images_per_item;
+};
+
+static constexpr int kSimpleImages = 16; // images walked by one CTA of the simple kernel
+
+__global__ void __launch_bounds__(kThreads) k2_simple_kernel(const FastParams p) {
+    const int r = threadIdx.x & 7;
+    const int s = blockIdx.x * kBlocksPerCta + (threadIdx.x >> 3);
+    if(s >= p.drop.n_simple) return;
+    const uint32_t  e = __ldg(p.drop.list_simple + s);
+    const int       c = entry_comp(e);
+    const DropComp &dc = p.drop.comp[c];
+    const size_t    bi = (size_t)entry_row(e) * dc.wb + entry_col(e);
+    const uint32_t  meta = __ldg(dc.meta + bi);
+    const bool      opaque = meta_cls(meta) == CLS_OPAQUE;
+    const float     w4 = uniform_w4(meta_wdc(meta));
+    const int       row = p.block_y * dc.vs + entry_row(e), col = p.block_x * dc.hs + entry_col(e);
+
+    int   D[8];
+    float Df[8];
+    row_unpack(ld_row_keep(dc.D + bi * 64 + r * 8), D);
+#pragma unroll
+    for(int i = 0; i < 8; i++) Df[i] = (float)D[i];
+
+    const int i0 = blockIdx.y * kSimpleImages, i1 = min(p.n, i0 + kSimpleImages);
+    for(int img = i0; img < i1; img++) {
+        const mjx_image_desc_t &im = p.items[img];
+        const int               stride = im.stride_blocks[c];
+        if(row >= im.rows[c] || col >= stride) continue;
+        int16_t      *ip = reinterpret_cast<int16_t *>(im.plane[c]) + ((size_t)row * stride + col) * 64 + r * 8;
+        const float  *t = p.tables + ((size_t)img * p.drop.ncomp + c) * kTabFloats;
+        const float4 ra = __ldg(reinterpret_cast<const float4 *>(t + kTabRq + r * 8));
+        const float4 rb = __ldg(reinterpret_cast<const float4 *>(t + kTabRq + r * 8 + 4));
+        const float  rq[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+        Row8         out;
+        if(opaque) {
+            // trunc(D / q): |D| <= 2^15 so the biased reciprocal is exact (tests/test_host_emul.py)
+#pragma unroll
+            for(int i = 0; i < 4; i++)
+                out.w[i] = pack2_int16(trunc_f(Df[2 * i] * rq[2 * i]), trunc_f(Df[2 * i + 1] * rq[2 * i + 1]));
+        }
+        else {
+            int  I[8], o[8];
+            Row8 qr = ld_row_keep(&im.q[c][r * 8]);
+            row_unpack(ld_row_stream(ip), I);
+#pragma unroll
+            for(int i = 0; i < 8; i++) {
+                const int q = (int)((qr.w[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
+                o[i] = blend_uniform(I[i], D[i], q, rq[i], w4);
+            }
+            out = row_pack(o);
+        }
+        st_row_stream(ip, out);
+    }
+}
+
+// =========================================================================================
+// fast path, kernel 3: G blocks, thread per block
+// =========================================================================================
+
+static constexpr int kGWarps = 6;                      // warps per CTA, one CTA per SM
+static constexpr int kGThreads = kGWarps * 32;
+static constexpr int kInBytes = 32 * 128;              // one image's 32 blocks
+static constexpr int kF32Bytes = 32 * 256;             // 32 blocks of 64 floats
+static constexpr int kOffIn = 0;                       // 2 stages
+static constexpr int kOffStash = 2 * kInBytes;         // dequantised coefficients as float
+static constexpr int kOffA = kOffStash + kF32Bytes;    // pixel-domain alpha of the tile
+static constexpr int kOffDs = kOffA + kF32Bytes;       // prescaled overlay coefficients of the tile
+static constexpr int kOffAddr = kOffDs + kF32Bytes;    // 2 x 32 global addresses of the image blocks
+static constexpr int kWarpSmem = kOffAddr + 2 * 32 * 8;
+static constexpr int kGSmem = kGWarps * kWarpSmem;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// 16-byte chunk `c` of block `t` inside a buffer whose blocks are B bytes: XOR swizzle so that the
+// 8 threads of a quarter-warp, reading the same chunk of 8 consecutive blocks, hit 8 distinct
+// bank groups (the layout TMA calls SWIZZLE_128B)
+template <int B>
+__device__ __forceinline__ int swz(int t, int c) { return t * B + ((c ^ (t & 7)) << 4); }
+
+// sign-extend with PRMT, convert with the full-rate I2FP.F32.S32 (the compiler's I2F.S16 issues at 1/4 rate)
+__device__ __forceinline__ float s16lo(uint32_t w) { return (float)(int)__byte_perm(w, 0u, 0x9910u); }
+__device__ __forceinline__ float s16hi(uint32_t w) { return (float)((int32_t)w >> 16); }
+
+__global__ void __launch_bounds__(kGThreads, 1) k2_generic_kernel(const FastParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *ws = smem_raw + warp * kWarpSmem;
+    const unsigned ws32 = smem_u32(ws);
+
+    const int ntiles = (p.drop.n_generic + 31) >> 5;
+    const int nchunks = (p.n + p.images_per_item - 1) / p.images_per_item;
+    const int nitems = ntiles * nchunks;
+    int       cur_tile = -1;
+    // this thread's block of the current tile
+    int  my_c = 0, my_row = 0, my_col = 0;
+    bool my_valid = false;
+
+    for(;;) {
+        int item = 0;
+        if(lane == 0) item = (int)atomicAdd(p.counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if(item >= nitems) break;
+        const int tile = item / nchunks, chunk = item - tile * nchunks;
+        const int tile_n = min(32, p.drop.n_generic - tile * 32);
+
+        if(tile != cur_tile) {
+            cur_tile = tile;
+            __syncwarp();
+            my_valid = lane < tile_n;
+            if(my_valid) {
+                const uint32_t  e = __ldg(p.drop.list_generic + tile * 32 + lane);
+                const DropComp &dc = p.drop.comp[entry_comp(e)];
+                my_c = entry_comp(e);
+                my_row = p.block_y * dc.vs + entry_row(e);
+                my_col = p.block_x * dc.hs + entry_col(e);
+            }
+            // A and Ds of the tile: 2 x 8 KB contiguous in list order -> swizzled shared memory
+            const float *ga = p.drop.gA + (size_t)tile * 32 * 64, *gd = p.drop.gDs + (size_t)tile * 32 * 64;
+#pragma unroll 4
+            for(int j = 0; j < 16; j++) {
+                const int g = j * 32 + lane, t = g >> 4, c = g & 15;
+                if(t < tile_n) {
+                    cp_async16(ws32 + kOffA + swz<256>(t, c), ga + g * 4);
+                    cp_async16(ws32 + kOffDs + swz<256>(t, c), gd + g * 4);
+                }
+            }
+        }
+
+        const int i0 = chunk * p.images_per_item, i1 = min(p.n, i0 + p.images_per_item);
+        unsigned long long *addr = reinterpret_cast<unsigned long long *>(ws + kOffAddr);
+
+        // issue the loads of image `img` into stage `st` (addresses of the 32 blocks first)
+        auto prefetch = [&](int img, int st) {
+            const mjx_image_desc_t &im = p.items[img];
+            unsigned long long      a = 0;
+            if(my_valid && my_row < im.rows[my_c] && my_col < im.stride_blocks[my_c])
+                a = im.plane[my_c] + ((unsigned long long)my_row * im.stride_blocks[my_c] + my_col) * 128ull;
+            addr[st * 32 + lane] = a;
+            __syncwarp();
+#pragma unroll
+            for(int j = 0; j < 8; j++) {
+                const int                g = j * 32 + lane, t = g >> 3, c = g & 7;
+                const unsigned long long b = addr[st * 32 + t];
+                if(b) cp_async16(ws32 + kOffIn + st * kInBytes + swz<128>(t, c), reinterpret_cast<const void *>(b + c * 16));
+            }
+        };
+
+        prefetch(i0, 0);
+        cp_async_commit();
+        for(int img = i0; img < i1; img++) {
+            const int st = (img - i0) & 1;
+            if(img + 1 < i1) prefetch(img + 1, st ^ 1);
+            cp_async_commit();
+            cp_async_wait<1>(); // everything but the newest group: image `img` (and the tile) has landed
+            __syncwarp();
+
+            const bool active = addr[st * 32 + lane] != 0;
+            if(active) {
+                const float   *tab = p.tables + ((size_t)img * p.drop.ncomp + my_c) * kTabFloats;
+                unsigned char *in = ws + kOffIn + st * kInBytes;
+                float          x[64];
+#pragma unroll
+                for(int r = 0; r < 8; r++) {
+                    const uint4  w = *reinterpret_cast<const uint4 *>(in + swz<128>(lane, r));
+                    const float4 d0 = *reinterpret_cast<const float4 *>(ws + kOffDs + swz<256>(lane, 2 * r));
+                    const float4 d1 = *reinterpret_cast<const float4 *>(ws + kOffDs + swz<256>(lane, 2 * r + 1));
+                    const float4 s0 = __ldg(reinterpret_cast<const float4 *>(tab + kTabQs + r * 8));
+                    const float4 s1 = __ldg(reinterpret_cast<const float4 *>(tab + kTabQs + r * 8 + 4));
+                    const float4 f0 = __ldg(reinterpret_cast<const float4 *>(tab + kTabQf + r * 8));
+                    const float4 f1 = __ldg(reinterpret_cast<const float4 *>(tab + kTabQf + r * 8 + 4));
+                    const float  I[8] = {s16lo(w.x), s16hi(w.x), s16lo(w.y), s16hi(w.y), s16lo(w.z), s16hi(w.z), s16lo(w.w), s16hi(w.w)};
+                    const float  ds[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+                    const float  qs[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                    const float  qf[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+                    float        dq[8];
+#pragma unroll
+                    for(int k = 0; k < 8; k++) {
+                        x[8 * r + k] = fmaf(-I[k], qs[k], ds[k]); // (D - I*q) * prescale
+                        dq[k] = I[k] * qf[k];                     // I*q, exact in fp32
+                    }
+                    *reinterpret_cast<float4 *>(ws + kOffStash + swz<256>(lane, 2 * r)) = make_float4(dq[0], dq[1], dq[2], dq[3]);
+                    *reinterpret_cast<float4 *>(ws + kOffStash + swz<256>(lane, 2 * r + 1)) = make_float4(dq[4], dq[5], dq[6], dq[7]);
+                }
+#pragma unroll
+                for(int v = 0; v < 8; v++) idct8s<1>(x + 8 * v);
+#pragma unroll
+                for(int u = 0; u < 8; u++) idct8s<8>(x + u);
+#pragma unroll
+                for(int r = 0; r < 8; r++) {
+                    const float4 a0 = *reinterpret_cast<const float4 *>(ws + kOffA + swz<256>(lane, 2 * r));
+                    const float4 a1 = *reinterpret_cast<const float4 *>(ws + kOffA + swz<256>(lane, 2 * r + 1));
+                    x[8 * r + 0] *= a0.x, x[8 * r + 1] *= a0.y, x[8 * r + 2] *= a0.z, x[8 * r + 3] *= a0.w;
+                    x[8 * r + 4] *= a1.x, x[8 * r + 5] *= a1.y, x[8 * r + 6] *= a1.z, x[8 * r + 7] *= a1.w;
+                }
+#pragma unroll
+                for(int u = 0; u < 8; u++) fdct8s<8>(x + u);
+#pragma unroll
+                for(int v = 0; v < 8; v++) fdct8s<1>(x + 8 * v);
+                const float fsc[8] = MJX_FWD_SCALE_INIT;
+#pragma unroll
+                for(int r = 0; r < 8; r++) {
+                    const float4 q0 = *reinterpret_cast<const float4 *>(ws + kOffStash + swz<256>(lane, 2 * r));
+                    const float4 q1 = *reinterpret_cast<const float4 *>(ws + kOffStash + swz<256>(lane, 2 * r + 1));
+                    const float4 r0 = __ldg(reinterpret_cast<const float4 *>(tab + kTabRq + r * 8));
+                    const float4 r1 = __ldg(reinterpret_cast<const float4 *>(tab + kTabRq + r * 8 + 4));
+                    const float  dq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                    const float  rq[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                    float        o[8];
+#pragma unroll
+                    for(int k = 0; k < 8; k++) o[k] = requant_f(dq[k], x[8 * r + k] * (fsc[r] * fsc[k]), rq[k]);
+                    *reinterpret_cast<uint4 *>(in + swz<128>(lane, r)) =
+                        make_uint4(pack2_int16(o[0], o[1]), pack2_int16(o[2], o[3]), pack2_int16(o[4], o[5]), pack2_int16(o[6], o[7]));
+                }
+            }
+            __syncwarp();
+            // coalesced write-back: 8 lanes per block
+#pragma unroll
+            for(int j = 0; j < 8; j++) {
+                const int                g = j * 32 + lane, t = g >> 3, c = g & 7;
+                const unsigned long long b = addr[st * 32 + t];
+                if(b) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(ws + kOffIn + st * kInBytes + swz<128>(t, c));
+                    __stcs(reinterpret_cast<uint4 *>(b + c * 16), v);
+                }
+            }
+            __syncwarp();
+        }
+        cp_async_wait<0>();
+    }
+}
+
+// =========================================================================================
+// launcher
+// =========================================================================================
+
+size_t k2_scratch_bytes(int n, int ncomp) { return 256 + (size_t)n * ncomp * kTabFloats * sizeof(float); }
+
 cudaError_t launch_k2(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, const DropView &view, int block_x,
-                      int block_y) {
+                      int block_y, void *scratch, int strict, int sm_count, int *launches) {
     if(n <= 0 || view.total_blocks <= 0) return cudaSuccess;
-    K2Params p;
-    p.drop = view;
-    p.block_x = block_x;
-    p.block_y = block_y;
-    const unsigned gx = (unsigned)((view.total_blocks + kBlocksPerCta - 1) / kBlocksPerCta);
+    cudaError_t e;
+    if(strict) {
+        StrictParams p;
+        p.drop = view;
+        p.block_x = block_x;
+        p.block_y = block_y;
+        const unsigned gx = (unsigned)((view.total_blocks + kBlocksPerCta - 1) / kBlocksPerCta);
+        for(int first = 0; first < n; first += 65535) {
+            const int cnt = n - first < 65535 ? n - first : 65535;
+            p.items = items_dev + first;
+            k2_strict_kernel<<<dim3(gx, (unsigned)cnt), kThreads, 0, s>>>(p);
+            if((e = cudaGetLastError()) != cudaSuccess) return e;
+            if(launches) (*launches)++;
+        }
+        return cudaSuccess;
+    }
+    if(view.n_simple == 0 && view.n_generic == 0) return cudaSuccess;
+
+    static bool attr_set = false; // idempotent; a benign race at worst sets it twice
+    if(!attr_set) {
+        if((e = cudaFuncSetAttribute(k2_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmem)) != cudaSuccess) return e;
+        attr_set = true;
+    }
     for(int first = 0; first < n; first += 65535) {
-        const int cnt = n - first < 65535 ? n - first : 65535;
+        const int     cnt = n - first < 65535 ? n - first : 65535;
+        unsigned int *counter = reinterpret_cast<unsigned int *>(scratch);
+        float        *tables = reinterpret_cast<float *>(reinterpret_cast<char *>(scratch) + 256);
+        FastParams    p;
+        p.drop = view;
         p.items = items_dev + first;
-        k2_compose_kernel<<<dim3(gx, (unsigned)cnt), kThreads, 0, s>>>(p);
-        cudaError_t e = cudaGetLastError();
-        if(e != cudaSuccess) return e;
+        p.tables = tables;
+        p.counter = counter;
+        p.n = cnt;
+        p.block_x = block_x;
+        p.block_y = block_y;
+        p.images_per_item = cnt < 32 ? cnt : 32;
+
+        k2_tables_kernel<<<dim3((unsigned)cnt, (unsigned)view.ncomp), 64, 0, s>>>(p.items, view.ncomp, tables);
+        if((e = cudaGetLastError()) != cudaSuccess) return e;
+        if(launches) (*launches)++;
+        if(view.n_simple > 0) {
+            const dim3 grid((unsigned)((view.n_simple + kBlocksPerCta - 1) / kBlocksPerCta), (unsigned)((cnt + kSimpleImages - 1) / kSimpleImages));
+            k2_simple_kernel<<<grid, kThreads, 0, s>>>(p);
+            if((e = cudaGetLastError()) != cudaSuccess) return e;
+            if(launches) (*launches)++;
+        }
+        if(view.n_generic > 0) {
+            if((e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), s)) != cudaSuccess) return e;
+            const int ntiles = (view.n_generic + 31) / 32;
+            const int nitems = ntiles * ((cnt + p.images_per_item - 1) / p.images_per_item);
+            int       ctas = (nitems + kGWarps - 1) / kGWarps;
+            const int sms = sm_count > 0 ? sm_count : 148;
+            if(ctas > sms) ctas = sms;
+            k2_generic_kernel<<<ctas, kGThreads, kGSmem, s>>>(p);
+            if((e = cudaGetLastError()) != cudaSuccess) return e;
+            if(launches) (*launches)++;
+        }
     }
     return cudaSuccess;
 }

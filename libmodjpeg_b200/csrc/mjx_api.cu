@@ -40,6 +40,8 @@ static int grow(mjx_ctx *ctx, void **p, size_t *have, size_t want, bool pinned) 
 int ensure_pin(mjx_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->pin, &ctx->pin_bytes, bytes, true); }
 int ensure_dev(mjx_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->dev, &ctx->dev_bytes, bytes, false); }
 int ensure_desc(mjx_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->desc_dev, &ctx->desc_bytes, bytes, false); }
+int ensure_scratch(mjx_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->scratch, &ctx->scratch_bytes, bytes, false); }
+int list_chunks(int total_blocks);
 
 static int use_device(mjx_ctx *ctx) {
     if(!ctx) return MJX_ERR_ARG;
@@ -98,11 +100,11 @@ void mjx_ctx_destroy(mjx_ctx *ctx) {
             cudaStreamSynchronize(ctx->pipe[i]);
             cudaStreamDestroy(ctx->pipe[i]);
         }
-        if(ctx->pipe_done[i]) cudaEventDestroy(ctx->pipe_done[i]);
     }
     if(ctx->pin) cudaFreeHost(ctx->pin);
     if(ctx->dev) cudaFree(ctx->dev);
     if(ctx->desc_dev) cudaFree(ctx->desc_dev);
+    if(ctx->scratch) cudaFree(ctx->scratch);
     if(ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -274,6 +276,52 @@ static int dropon_alloc(mjx_ctx *ctx, mjx_dropon **out, const mjx_layout_t *L, c
     return MJX_OK;
 }
 
+// second half of a compile: read the class counts back, size and fill the work lists and the
+// compact generic-class arrays (k1_lists.cu).  Synchronises the stream (one-time per dropon).
+static int dropon_finish(mjx_ctx *ctx, mjx_dropon *d) {
+    unsigned long long *cnt_dev = nullptr;
+    MJX_CUDA(ctx, cudaMalloc(&cnt_dev, 4 * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(cnt_dev, 0, 4 * sizeof(unsigned long long), ctx->stream);
+    if(e == cudaSuccess) e = launch_count_classes(ctx->stream, d, cnt_dev);
+    ctx->launches += d->view.ncomp;
+    unsigned long long h[4] = {0, 0, 0, 0};
+    if(e == cudaSuccess) e = cudaMemcpyAsync(h, cnt_dev, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+    if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(cnt_dev);
+    if(e != cudaSuccess) return fail(ctx, e, "count classes");
+    for(int i = 0; i < 4; i++) d->counts[i] = (long long)h[i];
+
+    const size_t n_simple = (size_t)(h[MJX_CLS_U] + h[MJX_CLS_OPAQUE]), n_generic = (size_t)h[MJX_CLS_G];
+    const size_t nchunks = (size_t)list_chunks(d->view.total_blocks);
+    size_t       off = 0;
+    const size_t off_chunks = off;
+    off = align_up(off + nchunks * 2 * sizeof(uint32_t), 256);
+    const size_t off_ls = off;
+    off = align_up(off + n_simple * sizeof(uint32_t), 256);
+    const size_t off_lg = off;
+    off = align_up(off + n_generic * sizeof(uint32_t), 256);
+    const size_t off_ds = off;
+    off = align_up(off + n_generic * 256, 256);
+    const size_t off_a = off;
+    off = align_up(off + n_generic * 256, 256);
+    d->slab2_bytes = off ? off : 256;
+    e = cudaMalloc(&d->slab2, d->slab2_bytes);
+    if(e != cudaSuccess) return fail(ctx, e, "cudaMalloc(compiled dropon lists)");
+    char *base = (char *)d->slab2;
+    d->view.list_simple = (const uint32_t *)(base + off_ls);
+    d->view.list_generic = (const uint32_t *)(base + off_lg);
+    d->view.n_simple = (int)n_simple;
+    d->view.n_generic = (int)n_generic;
+    d->view.gDs = (const float *)(base + off_ds);
+    d->view.gA = (const float *)(base + off_a);
+    int launches = 0;
+    e = launch_build_lists(ctx->stream, d, (uint32_t *)(base + off_chunks), &launches);
+    ctx->launches += launches;
+    if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if(e != cudaSuccess) return fail(ctx, e, "build work lists");
+    return MJX_OK;
+}
+
 int mjx_dropon_compile(mjx_ctx *ctx, mjx_dropon **out, const uint8_t *image3, const uint8_t *alpha3, int width,
                        int height, int dropon_colorspace, const mjx_layout_t *layout, int blockoffset_x,
                        int blockoffset_y, int crop_x, int crop_y, int crop_w, int crop_h, int pixels_on_device) {
@@ -338,6 +386,10 @@ int mjx_dropon_compile(mjx_ctx *ctx, mjx_dropon **out, const uint8_t *image3, co
         mjx_dropon_free(d);
         return fail(ctx, e, "k1_compile_kernel");
     }
+    if((rv = dropon_finish(ctx, d)) != MJX_OK) {
+        mjx_dropon_free(d);
+        return rv;
+    }
     *out = d;
     return MJX_OK;
 }
@@ -371,16 +423,19 @@ int mjx_dropon_from_coefficients(mjx_ctx *ctx, mjx_dropon **out, const mjx_layou
         mjx_dropon_free(d);
         return fail(ctx, e, "mjx_dropon_from_coefficients");
     }
+    if((rv = dropon_finish(ctx, d)) != MJX_OK) {
+        mjx_dropon_free(d);
+        return rv;
+    }
     *out = d;
     return MJX_OK;
 }
 
 void mjx_dropon_free(mjx_dropon *d) {
     if(!d) return;
-    if(d->slab) {
-        cudaSetDevice(d->device);
-        cudaFree(d->slab);
-    }
+    cudaSetDevice(d->device);
+    if(d->slab) cudaFree(d->slab);
+    if(d->slab2) cudaFree(d->slab2);
     delete d;
 }
 
@@ -411,27 +466,16 @@ int mjx_dropon_download(mjx_ctx *ctx, const mjx_dropon *d, int comp, int16_t *D,
     return MJX_OK;
 }
 
-int mjx_dropon_class_counts(mjx_ctx *ctx, const mjx_dropon *dc, long long counts[4]) {
-    int rv = use_device(ctx);
-    if(rv) return rv;
-    if(!dc || !counts) return MJX_ERR_ARG;
-    mjx_dropon *d = const_cast<mjx_dropon *>(dc);
-    std::lock_guard<std::mutex> lock(d->counts_mu);
-    if(!d->counts_valid) {
-        unsigned long long *dev = nullptr;
-        MJX_CUDA(ctx, cudaMalloc(&dev, 4 * sizeof(unsigned long long)));
-        cudaError_t e = cudaMemsetAsync(dev, 0, 4 * sizeof(unsigned long long), ctx->stream);
-        if(e == cudaSuccess) e = launch_count_classes(ctx->stream, d, dev);
-        ctx->launches += d->view.ncomp;
-        unsigned long long h[4] = {0, 0, 0, 0};
-        if(e == cudaSuccess) e = cudaMemcpyAsync(h, dev, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
-        if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        cudaFree(dev);
-        if(e != cudaSuccess) return fail(ctx, e, "count classes");
-        for(int i = 0; i < 4; i++) d->counts[i] = (long long)h[i];
-        d->counts_valid = true;
-    }
+int mjx_dropon_class_counts(mjx_ctx *ctx, const mjx_dropon *d, long long counts[4]) {
+    (void)ctx;
+    if(!d || !counts) return MJX_ERR_ARG;
     for(int i = 0; i < 4; i++) counts[i] = d->counts[i];
+    return MJX_OK;
+}
+
+int mjx_ctx_set_strict(mjx_ctx *ctx, int strict) {
+    if(!ctx) return MJX_ERR_ARG;
+    ctx->strict = strict ? 1 : 0;
     return MJX_OK;
 }
 
@@ -445,8 +489,10 @@ int mjx_compose_batch_device(mjx_ctx *ctx, const mjx_image_desc_t *items_dev, in
     if(rv) return rv;
     if(!items_dev || !d || n < 0 || block_x < 0 || block_y < 0) return MJX_ERR_ARG;
     if(d->device != ctx->device) return MJX_ERR_ARG;
-    cudaError_t e = launch_k2(ctx->stream, items_dev, n, d->view, block_x, block_y);
-    ctx->launches += (n + 65534) / 65535;
+    if((rv = ensure_scratch(ctx, k2_scratch_bytes(n < 65535 ? n : 65535, d->view.ncomp))) != MJX_OK) return rv;
+    int         launches = 0;
+    cudaError_t e = launch_k2(ctx->stream, items_dev, n, d->view, block_x, block_y, ctx->scratch, ctx->strict, ctx->sm_count, &launches);
+    ctx->launches += launches;
     if(e != cudaSuccess) return fail(ctx, e, "k2_compose_kernel");
     return MJX_OK;
 }
@@ -483,8 +529,10 @@ int mjx_compose_rows_host(mjx_ctx *ctx, int ncomp, int16_t *const *const *rows, 
     }
     MJX_CUDA(ctx, cudaMemcpyAsync(dev, pin, total, cudaMemcpyHostToDevice, ctx->stream));
     // the staged region starts at the dropon's origin: MCU position (0, 0)
-    cudaError_t e = launch_k2(ctx->stream, (const mjx_image_desc_t *)dev, 1, d->view, 0, 0);
-    ctx->launches++;
+    if((rv = ensure_scratch(ctx, k2_scratch_bytes(1, ncomp))) != MJX_OK) return rv;
+    int         launches = 0;
+    cudaError_t e = launch_k2(ctx->stream, (const mjx_image_desc_t *)dev, 1, d->view, 0, 0, ctx->scratch, ctx->strict, ctx->sm_count, &launches);
+    ctx->launches += launches;
     if(e != cudaSuccess) return fail(ctx, e, "k2_compose_kernel");
     const size_t head = align_up(sizeof(mjx_image_desc_t), 256);
     MJX_CUDA(ctx, cudaMemcpyAsync(pin + head, dev + head, total - head, cudaMemcpyDeviceToHost, ctx->stream));
@@ -499,7 +547,6 @@ int mjx_compose_rows_host(mjx_ctx *ctx, int ncomp, int16_t *const *const *rows, 
 static int pipe_init(mjx_ctx *ctx) {
     for(int i = 0; i < mjx_ctx::kPipe; i++) {
         if(!ctx->pipe[i]) MJX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->pipe[i], cudaStreamNonBlocking));
-        if(!ctx->pipe_done[i]) MJX_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_done[i], cudaEventDisableTiming));
     }
     return MJX_OK;
 }
@@ -527,7 +574,8 @@ int mjx_compose_batch_host(mjx_ctx *ctx, const mjx_host_image_t *items, int n, c
     }
     const int    P = mjx_ctx::kPipe;
     const size_t desc_sz = align_up(sizeof(mjx_image_desc_t), 256);
-    if((rv = pipe_init(ctx)) || (rv = ensure_dev(ctx, slot * P)) || (rv = ensure_desc(ctx, desc_sz * P)) ||
+    const size_t scr_sz = align_up(k2_scratch_bytes(1, ncomp), 256);
+    if((rv = pipe_init(ctx)) || (rv = ensure_dev(ctx, slot * P)) || (rv = ensure_desc(ctx, desc_sz * P)) || (rv = ensure_scratch(ctx, scr_sz * P)) ||
        (rv = ensure_pin(ctx, desc_sz * (size_t)n)))
         return rv;
     char *dev = (char *)ctx->dev, *pin = (char *)ctx->pin, *ddev = (char *)ctx->desc_dev;
@@ -562,8 +610,10 @@ int mjx_compose_batch_host(mjx_ctx *ctx, const mjx_host_image_t *items, int n, c
             if(sp == wbytes) MJX_CUDA(ctx, cudaMemcpyAsync(base + off[c], src, wbytes * dc.hb, cudaMemcpyHostToDevice, st));
             else MJX_CUDA(ctx, cudaMemcpy2DAsync(base + off[c], wbytes, src, sp, wbytes, dc.hb, cudaMemcpyHostToDevice, st));
         }
-        cudaError_t e = launch_k2(st, (const mjx_image_desc_t *)(ddev + desc_sz * s), 1, d->view, 0, 0);
-        ctx->launches++;
+        int         launches = 0;
+        cudaError_t e = launch_k2(st, (const mjx_image_desc_t *)(ddev + desc_sz * s), 1, d->view, 0, 0, (char *)ctx->scratch + scr_sz * s,
+                                  ctx->strict, ctx->sm_count, &launches);
+        ctx->launches += launches;
         if(e != cudaSuccess) return fail(ctx, e, "k2_compose_kernel");
         for(int c = 0; c < ncomp; c++) {
             const DropComp &dc = d->view.comp[c];

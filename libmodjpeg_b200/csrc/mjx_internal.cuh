@@ -23,11 +23,32 @@ struct DropComp {
     int start;            // index of this component's first block in the flattened block list
 };
 
+// Work lists written by K1 so that K2 never visits a transparent block and never mixes classes
+// in a warp.  An entry locates one dropon block: comp << 30 | row << 15 | col (dropon-relative),
+// row-major within a component, components in order.
 struct DropView {
-    DropComp comp[MJX_MAX_COMPONENTS];
-    int      ncomp;
-    int      total_blocks;
+    DropComp        comp[MJX_MAX_COMPONENTS];
+    int             ncomp;
+    int             total_blocks;
+    const uint32_t *list_simple;  // OPAQUE and U blocks
+    const uint32_t *list_generic; // G blocks
+    int             n_simple, n_generic;
+    const float    *gDs; // [n_generic][64] overlay coefficients * IDCT prescale (natural order)
+    const float    *gA;  // [n_generic][64] pixel-domain alpha / 255 = IDCT2(W) / 255
 };
+
+static inline __host__ __device__ uint32_t entry_pack(int comp, int row, int col) {
+    return ((uint32_t)comp << 30) | ((uint32_t)row << 15) | (uint32_t)col;
+}
+static inline __host__ __device__ int entry_comp(uint32_t e) { return (int)(e >> 30); }
+static inline __host__ __device__ int entry_row(uint32_t e) { return (int)((e >> 15) & 0x7fffu); }
+static inline __host__ __device__ int entry_col(uint32_t e) { return (int)(e & 0x7fffu); }
+
+// per (image, component) float tables K2 reads instead of converting q on the fly
+static const int kTabQf = 0;   // (float) q
+static const int kTabQs = 64;  // q * IDCT prescale
+static const int kTabRq = 128; // biased reciprocal, see quant_rcp()
+static const int kTabFloats = 192;
 
 } // namespace mjx
 
@@ -35,15 +56,15 @@ struct DropView {
 struct mjx_dropon {
     int            device = 0;
     mjx_layout_t   layout{};
-    void          *slab = nullptr; // one allocation holding every plane below
+    void          *slab = nullptr;  // D, W, meta of every component
     size_t         slab_bytes = 0;
+    void          *slab2 = nullptr; // work lists + compact generic-class arrays
+    size_t         slab2_bytes = 0;
     mjx::DropView  view{};
     int16_t       *D[MJX_MAX_COMPONENTS] = {};
     int16_t       *W[MJX_MAX_COMPONENTS] = {};
     uint32_t      *meta[MJX_MAX_COMPONENTS] = {};
-    std::mutex     counts_mu;
-    bool           counts_valid = false;
-    long long      counts[4] = {};
+    long long      counts[4] = {}; // blocks per class, all components
 };
 
 struct mjx_ctx {
@@ -53,6 +74,7 @@ struct mjx_ctx {
     std::string  last_error;
     long long    launches = 0;
     int          sm_count = 0;
+    int          strict = 0; // 1: one kernel for every class with the reference's int16 wrap-around
 
     // staging pools for the host-pointer entry points (grown on demand, reused across calls)
     void  *pin = nullptr;
@@ -61,11 +83,12 @@ struct mjx_ctx {
     size_t dev_bytes = 0;
     void  *desc_dev = nullptr; // device array of mjx_image_desc_t for staged launches
     size_t desc_bytes = 0;
+    void  *scratch = nullptr; // per-launch K2 scratch: float tables + work counters
+    size_t scratch_bytes = 0;
 
-    // extra streams + events for the pipelined batch-host path
+    // extra streams for the pipelined batch-host path
     static const int kPipe = 3;
     cudaStream_t pipe[kPipe] = {};
-    cudaEvent_t  pipe_done[kPipe] = {};
 };
 
 namespace mjx {
@@ -74,17 +97,23 @@ int  fail(mjx_ctx *ctx, cudaError_t e, const char *what);
 int  ensure_pin(mjx_ctx *ctx, size_t bytes);
 int  ensure_dev(mjx_ctx *ctx, size_t bytes);
 int  ensure_desc(mjx_ctx *ctx, size_t bytes);
+int  ensure_scratch(mjx_ctx *ctx, size_t bytes);
 
-// kernel launchers (each returns a cudaError_t from the launch)
+// bytes of scratch one K2 launch over n images needs
+size_t k2_scratch_bytes(int n, int ncomp);
+
+// kernel launchers (each returns a cudaError_t from the launch; *launches += kernels launched)
 cudaError_t launch_k1(cudaStream_t s, const uint8_t *image3, const uint8_t *alpha3, int dw, int dh, int dropon_cs,
                       int target_cs, int boff_x, int boff_y, int crop_x, int crop_y, int crop_w, int crop_h,
                       int canvas_w, int canvas_h, int max_h, int max_v, mjx_dropon *d);
 cudaError_t launch_classify(cudaStream_t s, mjx_dropon *d);
+cudaError_t launch_count_classes(cudaStream_t s, const mjx_dropon *d, unsigned long long *counts_dev);
+// after classification: fill the work lists and the compact generic-class arrays (slab2 allocated)
+cudaError_t launch_build_lists(cudaStream_t s, mjx_dropon *d, uint32_t *chunk_counts_dev, int *launches);
 cudaError_t launch_k2(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, const DropView &view, int block_x,
-                      int block_y);
+                      int block_y, void *scratch, int strict, int sm_count, int *launches);
 cudaError_t launch_k3(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, int ncomp, const mjx_effect_op_t *ops,
                       int nops, int *launches);
-cudaError_t launch_count_classes(cudaStream_t s, const mjx_dropon *d, unsigned long long *counts_dev);
 
 } // namespace mjx
 

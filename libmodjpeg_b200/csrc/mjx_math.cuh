@@ -8,7 +8,9 @@
 // compare it with the oracle on the CPU box (test aid only -- the product has no CPU path).
 #pragma once
 
+#include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define MJX_HD __host__ __device__ __forceinline__
@@ -217,6 +219,93 @@ MJX_HD void fdct8_islow(int *d) {
 
 // quality-100 quantisation of an islow output (divisor 8): sign(x) * ((|x| + 4) >> 3)
 MJX_HD int quant_q1(int x) { return x < 0 ? -((-x + 4) >> 3) : ((x + 4) >> 3); }
+
+// ---------------------------------------------------------------------------------------
+// whole-block (thread-per-block) arithmetic of the generic class.  The same AAN flow graphs as
+// idct8/fdct8 but on strided register arrays so a thread can transform rows (S = 1) and
+// columns (S = 8) of its 64 registers without any transpose, written so that multiply+add
+// pairs contract to FFMA.  No int<->float conversion instructions are used on the hot path:
+// on sm_100a F2I/FRND issue at 1/8 rate and I2F.S16 / SHFL at 1/4 (profiles/microbench).
+// ---------------------------------------------------------------------------------------
+template <int S>
+MJX_HD void idct8s(float *v) {
+    float t10 = v[0] + v[4 * S], t11 = v[0] - v[4 * S];
+    float t13 = v[2 * S] + v[6 * S], t12 = (v[2 * S] - v[6 * S]) * 1.414213562373095049f - t13;
+    float t0 = t10 + t13, t3 = t10 - t13, t1 = t11 + t12, t2 = t11 - t12;
+    float z13 = v[5 * S] + v[3 * S], z10 = v[5 * S] - v[3 * S], z11 = v[S] + v[7 * S], z12 = v[S] - v[7 * S];
+    float t7 = z11 + z13;
+    float z5 = (z10 + z12) * 1.847759065022573512f;
+    float t6 = (z5 - z10 * 2.613125929752753056f) - t7;
+    float t5 = (z11 - z13) * 1.414213562373095049f - t6;
+    float t4 = (z5 - z12 * 1.082392200292393968f) - t5;
+    v[0] = t0 + t7;
+    v[7 * S] = t0 - t7;
+    v[S] = t1 + t6;
+    v[6 * S] = t1 - t6;
+    v[2 * S] = t2 + t5;
+    v[5 * S] = t2 - t5;
+    v[3 * S] = t3 + t4;
+    v[4 * S] = t3 - t4;
+}
+
+template <int S>
+MJX_HD void fdct8s(float *v) {
+    float t0 = v[0] + v[7 * S], t7 = v[0] - v[7 * S], t1 = v[S] + v[6 * S], t6 = v[S] - v[6 * S];
+    float t2 = v[2 * S] + v[5 * S], t5 = v[2 * S] - v[5 * S], t3 = v[3 * S] + v[4 * S], t4 = v[3 * S] - v[4 * S];
+    float t10 = t0 + t3, t13 = t0 - t3, t11 = t1 + t2, t12 = t1 - t2;
+    v[0] = t10 + t11;
+    v[4 * S] = t10 - t11;
+    float z1 = (t12 + t13) * 0.707106781186547524f;
+    v[2 * S] = t13 + z1;
+    v[6 * S] = t13 - z1;
+    t10 = t4 + t5;
+    t11 = t5 + t6;
+    t12 = t6 + t7;
+    float z5 = (t10 - t12) * 0.382683432365089772f;
+    float z2 = 0.541196100146196985f * t10 + z5;
+    float z4 = 1.306562964876376527f * t12 + z5;
+    float z11 = t7 + t11 * 0.707106781186547524f, z13 = t7 - t11 * 0.707106781186547524f;
+    v[5 * S] = z13 + z2;
+    v[3 * S] = z13 - z2;
+    v[S] = z11 + z4;
+    v[7 * S] = z11 - z4;
+}
+
+// truncation toward zero that stays in the fp32 pipe: |v| + 2^23 rounded toward zero has ulp 1,
+// so it is 2^23 + floor(|v|); exact for |v| < 2^23.  (== (float)(int)v, the reference's (int)Y.)
+MJX_HD float trunc_f(float v) {
+#if defined(__CUDA_ARCH__)
+    const float m = __fadd_rz(fabsf(v), 8388608.0f) - 8388608.0f;
+    return copysignf(m, v);
+#else
+    return (float)(int)v;
+#endif
+}
+
+// low 16 bits of (integer-valued float o + 1.5*2^23) are o as a two's-complement int16
+MJX_HD uint32_t int16_bits_of(float o) {
+    const float  biased = o + 12582912.0f;
+    uint32_t     u;
+#if defined(__CUDA_ARCH__)
+    u = __float_as_uint(biased);
+#else
+    memcpy(&u, &biased, 4);
+#endif
+    return u;
+}
+
+MJX_HD uint32_t pack2_int16(float lo, float hi) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(int16_bits_of(lo), int16_bits_of(hi), 0x5410);
+#else
+    return (int16_bits_of(lo) & 0xffffu) | (int16_bits_of(hi) << 16);
+#endif
+}
+
+// requantisation of one generic coefficient in the fp32 pipe: (deq + (int)Y) / q, truncating.
+// Equal to tdiv(deq + (int)Y, rq) whenever no int16 wrap-around occurs (|deq + Y| < 32768),
+// which holds for every JPEG a conforming encoder produces; the strict kernel keeps the wraps.
+MJX_HD float requant_f(float deq_f, float Y, float rq) { return trunc_f((deq_f + trunc_f(Y)) * rq); }
 
 // libjpeg-turbo jccolor.c RGB -> YCbCr, 16-bit fixed point
 MJX_HD int rgb_to_y(int r, int g, int b) { return (19595 * r + 38470 * g + 7471 * b + 32768) >> 16; }

@@ -22,6 +22,10 @@ long long emul_tdiv_check(int qmin, int qmax) {
     return bad;
 }
 
+static int g_generic_v2 = 0;
+void emul_set_generic_v2(int on) { g_generic_v2 = on; }
+void emul_generic_block_v2(int16_t *I, const int16_t *D, const int16_t *W, const uint16_t *q);
+
 static void transpose(float m[8][8]) {
     for(int i = 0; i < 8; i++)
         for(int j = i + 1; j < 8; j++) {
@@ -55,6 +59,10 @@ int emul_compose_block(int16_t *I, const int16_t *D, const int16_t *W, const uin
         for(int i = 0; i < 64; i++) I[i] = (int16_t)blend_uniform(I[i], D[i], q[i], rq[i], w4);
         return (int)cls;
     }
+    if(g_generic_v2) {
+        emul_generic_block_v2(I, D, W, q);
+        return (int)cls;
+    }
     float x[8][8], a[8][8];
     int   deq[64];
     for(int r = 0; r < 8; r++)
@@ -78,6 +86,36 @@ int emul_compose_block(int16_t *I, const int16_t *D, const int16_t *W, const uin
             I[8 * r + i] = (int16_t)tdiv(wrap16(deq[8 * r + i] + f2i_trunc(Y)), rq[8 * r + i]);
         }
     return (int)cls;
+}
+
+// the generic class as the thread-per-block kernel computes it (k2 generic kernel): float tables
+// qs = q*s, qf = q, rq; dropon side Ds = D*s and pixel-domain alpha A = IDCT2(W*s/255); fp32-pipe
+// requantisation without int<->float conversions.
+void emul_generic_block_v2(int16_t *I, const int16_t *D, const int16_t *W, const uint16_t *q) {
+    float x[64], A[64], deq[64];
+    for(int v = 0; v < 8; v++)
+        for(int u = 0; u < 8; u++) {
+            const int   i = 8 * v + u;
+            const float s = inv_scale(v) * inv_scale(u);
+            const float Ds = (float)D[i] * s, qs = (float)q[i] * s, qf = (float)q[i];
+            A[i] = (float)W[i] * (s * (1.0f / 255.0f));
+            deq[i] = (float)I[i] * qf;
+            x[i] = Ds - (float)I[i] * qs;
+        }
+    for(int v = 0; v < 8; v++) idct8s<1>(A + 8 * v), idct8s<1>(x + 8 * v);
+    for(int u = 0; u < 8; u++) idct8s<8>(A + u), idct8s<8>(x + u);
+    for(int i = 0; i < 64; i++) x[i] *= A[i];
+    for(int u = 0; u < 8; u++) fdct8s<8>(x + u);
+    for(int v = 0; v < 8; v++) fdct8s<1>(x + 8 * v);
+    for(int v = 0; v < 8; v++)
+        for(int u = 0; u < 8; u += 2) {
+            const int   i = 8 * v + u;
+            const float o0 = requant_f(deq[i], x[i] * (fwd_scale(v) * fwd_scale(u)), quant_rcp(q[i]));
+            const float o1 = requant_f(deq[i + 1], x[i + 1] * (fwd_scale(v) * fwd_scale(u + 1)), quant_rcp(q[i + 1]));
+            const uint32_t pk = pack2_int16(o0, o1);
+            I[i] = (int16_t)(pk & 0xffffu);
+            I[i + 1] = (int16_t)(pk >> 16);
+        }
 }
 
 void emul_compose_plane(int16_t *plane, int stride_blocks, int x0, int y0, const int16_t *Dp, const int16_t *Wp, int wb,

@@ -431,3 +431,64 @@ def test_api_threads_are_independent(engine):
     for k in range(2, 6):
         for a, b in zip(results[k], results[k % 2]):
             assert np.array_equal(a, b)
+
+
+def test_k2_strict_mode_reproduces_int16_wraparound(engine, port):
+    """adversarial coefficients (|I*q| far outside int16): the strict kernel follows the reference's
+    wrap-around bit for bit on T/U/OPAQUE blocks and to +-1 step on G blocks."""
+    from libmodjpeg_b200 import Layout
+    from oracle import oracle_py as O
+
+    rng = np.random.default_rng(5)
+    samp = [(1, 1)] * 3
+    planes = [rng.integers(-2047, 2048, (12, 16, 64)).astype(np.int16) for _ in range(3)]
+    q = [rng.integers(20, 256, 64).astype(np.uint16) for _ in range(3)]
+    try:
+        engine.set_strict(True)
+        for name, raw, cs, blend in [("uniform", util.noisy_rgba(96, 64, 1)[:, :, :3], 1, 100), ("opaque", util.noisy_rgba(96, 64, 2)[:, :, :3], 1, 255),
+                                     ("generic", util.noisy_rgba(96, 64, 3), 2, 255)]:
+            i3, a3, scs, sblend = util.ingest_raw(raw, cs, blend)
+            rv, D, Wc = port.compile_dropon(i3, a3, scs, O.make_layout(3, samp))
+            assert rv == 0
+            cd = engine.dropon_compile(i3, a3, scs, Layout.make(3, samp))
+            want = [p.copy() for p in planes]
+            for c in range(3):
+                port.compose_plane(want[c], 2, 1, D[c], Wc[c], q[c])
+            got = [p.copy() for p in planes]
+            engine.compose_planes_host(got, q, cd, 2, 1)
+            n = bad = 0
+            for c in range(3):
+                dd = got[c].astype(np.int32) - want[c].astype(np.int32)
+                if name != "generic":
+                    assert not dd.any(), (name, c)
+                n += dd.size
+                bad += int((dd != 0).sum())
+            assert bad <= n * 1e-3, (name, bad, n)
+            cd.free()
+    finally:
+        engine.set_strict(False)
+
+
+def test_k2_fast_equals_strict_on_encoder_produced_jpegs(engine):
+    """the fast kernels (work lists, thread-per-block, fp32-pipe requantisation) and the strict
+    kernel agree bit for bit outside class G and to +-1 step inside, on real JPEG coefficients"""
+    from libmodjpeg_b200 import Layout, capi
+
+    for subs in ("420", "444"):
+        j, info, samp, planes, q = _decode(util.jpeg_bytes(400, 304, subs, 85, seed=91))
+        raw = util.logo_rgba(320, 240, 64, 27)
+        i3, a3, scs, blend = util.ingest_raw(raw, 2, 255)
+        g = capi.geometry(info["width"], info["height"], info["max_h"] * 8, info["max_v"] * 8, 320, 240, 16, 7, 5)
+        cd = engine.dropon_compile(i3, a3, scs, Layout.make(3, samp), (g["blockoffset_x"], g["blockoffset_y"]),
+                                   (g["crop_x"], g["crop_y"], g["crop_w"], g["crop_h"]))
+        fast = [p.copy() for p in planes]
+        engine.compose_planes_host(fast, q, cd, g["block_x"], g["block_y"])
+        try:
+            engine.set_strict(True)
+            strict = [p.copy() for p in planes]
+            engine.compose_planes_host(strict, q, cd, g["block_x"], g["block_y"])
+        finally:
+            engine.set_strict(False)
+        cls_maps = [cd.download(c)[2] for c in range(3)]
+        _check_planes(fast, strict, planes, cls_maps, (g["block_x"], g["block_y"]), samp, ("fast-vs-strict", subs))
+        cd.free()
