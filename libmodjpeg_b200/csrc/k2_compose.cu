@@ -256,7 +256,13 @@ template <int B>
 __device__ __forceinline__ int swz(int t, int c) { return t * B + ((c ^ (t & 7)) << 4); }
 
 // sign-extend with PRMT, convert with the full-rate I2FP.F32.S32 (the compiler's I2F.S16 issues at 1/4 rate)
-__device__ __forceinline__ float s16lo(uint32_t w) { return (float)(int)__byte_perm(w, 0u, 0x9910u); }
+// (PTX prmt replicates the sign of a byte when bit 3 of its selector nibble is set; the
+// __byte_perm() intrinsic masks that bit off, hence the inline asm)
+__device__ __forceinline__ float s16lo(uint32_t w) {
+    int v;
+    asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(v) : "r"(w));
+    return (float)v;
+}
 __device__ __forceinline__ float s16hi(uint32_t w) { return (float)((int32_t)w >> 16); }
 
 __global__ void __launch_bounds__(kGThreads, 1) k2_generic_kernel(const FastParams p) {

@@ -473,6 +473,19 @@ int mjx_dropon_class_counts(mjx_ctx *ctx, const mjx_dropon *d, long long counts[
     return MJX_OK;
 }
 
+int mjx_dropon_download_generic(mjx_ctx *ctx, const mjx_dropon *d, uint32_t *list, float *Ds, float *A) {
+    int rv = use_device(ctx);
+    if(rv) return rv;
+    if(!d) return MJX_ERR_ARG;
+    const size_t n = (size_t)d->view.n_generic;
+    MJX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if(n == 0) return MJX_OK;
+    if(list) MJX_CUDA(ctx, cudaMemcpy(list, d->view.list_generic, n * 4, cudaMemcpyDeviceToHost));
+    if(Ds) MJX_CUDA(ctx, cudaMemcpy(Ds, d->view.gDs, n * 256, cudaMemcpyDeviceToHost));
+    if(A) MJX_CUDA(ctx, cudaMemcpy(A, d->view.gA, n * 256, cudaMemcpyDeviceToHost));
+    return MJX_OK;
+}
+
 int mjx_ctx_set_strict(mjx_ctx *ctx, int strict) {
     if(!ctx) return MJX_ERR_ARG;
     ctx->strict = strict ? 1 : 0;
