@@ -140,8 +140,11 @@ int  mjx_dropon_dims(const mjx_dropon *d, int comp, int *wb, int *hb);
 long long mjx_dropon_blocks(const mjx_dropon *d); /* all components */
 /* copy component `comp` back: D, W int16 [hb][wb][64]; cls uint8 [hb][wb] (any may be NULL) */
 int  mjx_dropon_download(mjx_ctx *ctx, const mjx_dropon *d, int comp, int16_t *D, int16_t *W, uint8_t *cls);
-/* the generic-class work list (n = counts[MJX_CLS_G] entries: comp << 30 | row << 15 | col) and, in list order,
- * Ds = D * IDCT prescale and A = pixel-domain alpha / 255, 64 floats per entry (any pointer may be NULL) */
+/* the generic-class work list: n = mjx_dropon_generic_slots() entries (comp << 30 | row << 15 | col; every component
+ * starts on a multiple of 32, padding slots hold 0xffffffff) and, in list order, Ds = D * IDCT prescale (natural order)
+ * and A = pixel-domain alpha / 255 stored row-paired: float (8i + k)*2 + h = A[row 2i + h][col k]; 64 floats per slot
+ * (any pointer may be NULL) */
+int  mjx_dropon_generic_slots(const mjx_dropon *d);
 int  mjx_dropon_download_generic(mjx_ctx *ctx, const mjx_dropon *d, uint32_t *list, float *Ds, float *A);
 /* counts[MJX_CLS_*] summed over all components */
 int  mjx_dropon_class_counts(mjx_ctx *ctx, const mjx_dropon *d, long long counts[4]);

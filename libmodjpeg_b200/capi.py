@@ -126,6 +126,7 @@ def load_mjx() -> C.CDLL:
     L.mjx_dropon_download.argtypes = [vp, vp, C.c_int, vp, vp, vp]
     L.mjx_dropon_class_counts.argtypes = [vp, vp, C.POINTER(C.c_longlong)]
     L.mjx_dropon_download_generic.argtypes = [vp, vp, vp, vp, vp]
+    L.mjx_dropon_generic_slots.argtypes = [vp]
     L.mjx_compose_batch_device.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int]
     L.mjx_compose_batch_host.argtypes = [vp, C.POINTER(HostImage), C.c_int, vp, C.c_int, C.c_int]
     L.mjx_compose_rows_host.argtypes = [vp, C.c_int, vp, vp, vp]
@@ -178,7 +179,7 @@ class CompiledDropon:
 
     def download_generic(self):
         """-> (entries uint32 [n], Ds float32 [n][64], A float32 [n][64]) of the generic-class list"""
-        n = self.class_counts()["G"]
+        n = int(self.engine.lib.mjx_dropon_generic_slots(self.handle))
         lst = np.zeros(n, np.uint32)
         Ds = np.zeros((n, 64), np.float32)
         A = np.zeros((n, 64), np.float32)

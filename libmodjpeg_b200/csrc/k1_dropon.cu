@@ -184,13 +184,14 @@ cudaError_t launch_classify(cudaStream_t s, mjx_dropon *d) {
     return cudaSuccess;
 }
 
+// counts_dev: [MJX_MAX_COMPONENTS][4] blocks per class, per component
 cudaError_t launch_count_classes(cudaStream_t s, const mjx_dropon *d, unsigned long long *counts_dev) {
     for(int c = 0; c < d->view.ncomp; c++) {
         const int nb = d->view.comp[c].wb * d->view.comp[c].hb;
         if(nb <= 0) continue;
         int grid = (nb + 255) / 256;
         if(grid > 1024) grid = 1024;
-        count_classes_kernel<<<grid, 256, 0, s>>>(d->meta[c], nb, counts_dev);
+        count_classes_kernel<<<grid, 256, 0, s>>>(d->meta[c], nb, counts_dev + 4 * c);
         cudaError_t e = cudaGetLastError();
         if(e != cudaSuccess) return e;
     }

@@ -17,6 +17,7 @@ struct ListParams {
     const uint32_t *meta[MJX_MAX_COMPONENTS];
     int             wb[MJX_MAX_COMPONENTS];
     int             start[MJX_MAX_COMPONENTS];
+    int             pad[MJX_MAX_COMPONENTS]; // slots inserted before component c's entries in the generic list
     int             ncomp, total_blocks;
 };
 
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(kChunk) list_fill_kernel(const ListParams p, c
     __syncthreads();
     const unsigned below = (1u << lane) - 1u;
     if(kind == 1) list_simple[chunk_offsets[2 * blockIdx.x] + warp_s[warp] + __popc(bs & below)] = e;
-    if(kind == 2) list_generic[chunk_offsets[2 * blockIdx.x + 1] + warp_g[warp] + __popc(bg & below)] = e;
+    if(kind == 2) list_generic[chunk_offsets[2 * blockIdx.x + 1] + warp_g[warp] + __popc(bg & below) + p.pad[entry_comp(e)]] = e;
 }
 
 // compact float arrays of the generic blocks; 8 lanes per block, lane r = row r
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(256) generic_prepare_kernel(const DropView dv,
     const int g = blockIdx.x * 32 + (threadIdx.x >> 3);
     if(g >= dv.n_generic) return;
     const uint32_t  e = __ldg(dv.list_generic + g);
+    if(e == 0xffffffffu) return; // padding slot (whole 8-lane group leaves)
     const DropComp &dc = dv.comp[entry_comp(e)];
     const size_t    bi = (size_t)entry_row(e) * dc.wb + entry_col(e);
     int             D[8], W[8];
@@ -117,9 +119,10 @@ __global__ void __launch_bounds__(256) generic_prepare_kernel(const DropView dv,
     float4 *o = reinterpret_cast<float4 *>(gDs + (size_t)g * 64 + r * 8);
     o[0] = make_float4(ds[0], ds[1], ds[2], ds[3]);
     o[1] = make_float4(ds[4], ds[5], ds[6], ds[7]);
-    o = reinterpret_cast<float4 *>(gA + (size_t)g * 64 + r * 8);
-    o[0] = make_float4(a[0], a[1], a[2], a[3]);
-    o[1] = make_float4(a[4], a[5], a[6], a[7]);
+    // A is stored "Q-paired" for k2_generic_kernel: float (8*i + k) * 2 + h  =  A[row 2i + h][col k]
+    float *ao = gA + (size_t)g * 64 + (size_t)(r >> 1) * 16 + (r & 1);
+#pragma unroll
+    for(int k = 0; k < 8; k++) ao[2 * k] = a[k];
 }
 
 cudaError_t launch_build_lists(cudaStream_t s, mjx_dropon *d, uint32_t *chunk_counts_dev, int *launches) {
@@ -133,6 +136,7 @@ cudaError_t launch_build_lists(cudaStream_t s, mjx_dropon *d, uint32_t *chunk_co
         p.meta[c] = d->meta[c];
         p.wb[c] = d->view.comp[c].wb > 0 ? d->view.comp[c].wb : 1;
         p.start[c] = d->view.comp[c].start;
+        p.pad[c] = d->generic_pad[c];
     }
     cudaError_t e;
     list_count_kernel<<<nchunks, kChunk, 0, s>>>(p, chunk_counts_dev);

@@ -279,19 +279,27 @@ static int dropon_alloc(mjx_ctx *ctx, mjx_dropon **out, const mjx_layout_t *L, c
 // second half of a compile: read the class counts back, size and fill the work lists and the
 // compact generic-class arrays (k1_lists.cu).  Synchronises the stream (one-time per dropon).
 static int dropon_finish(mjx_ctx *ctx, mjx_dropon *d) {
+    const int           NC = MJX_MAX_COMPONENTS * 4;
     unsigned long long *cnt_dev = nullptr;
-    MJX_CUDA(ctx, cudaMalloc(&cnt_dev, 4 * sizeof(unsigned long long)));
-    cudaError_t e = cudaMemsetAsync(cnt_dev, 0, 4 * sizeof(unsigned long long), ctx->stream);
+    MJX_CUDA(ctx, cudaMalloc(&cnt_dev, NC * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(cnt_dev, 0, NC * sizeof(unsigned long long), ctx->stream);
     if(e == cudaSuccess) e = launch_count_classes(ctx->stream, d, cnt_dev);
     ctx->launches += d->view.ncomp;
-    unsigned long long h[4] = {0, 0, 0, 0};
+    unsigned long long h[MJX_MAX_COMPONENTS * 4] = {};
     if(e == cudaSuccess) e = cudaMemcpyAsync(h, cnt_dev, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
     if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(cnt_dev);
     if(e != cudaSuccess) return fail(ctx, e, "count classes");
-    for(int i = 0; i < 4; i++) d->counts[i] = (long long)h[i];
-
-    const size_t n_simple = (size_t)(h[MJX_CLS_U] + h[MJX_CLS_OPAQUE]), n_generic = (size_t)h[MJX_CLS_G];
+    for(int i = 0; i < 4; i++) d->counts[i] = 0;
+    // the generic list is padded so that every component starts on a tile (32-entry) boundary
+    size_t n_simple = 0, n_generic = 0, g_blocks = 0;
+    for(int c = 0; c < d->view.ncomp; c++) {
+        for(int i = 0; i < 4; i++) d->counts[i] += (long long)h[4 * c + i];
+        n_simple += (size_t)(h[4 * c + MJX_CLS_U] + h[4 * c + MJX_CLS_OPAQUE]);
+        d->generic_pad[c] = (int)(n_generic - g_blocks);
+        g_blocks += (size_t)h[4 * c + MJX_CLS_G];
+        n_generic = align_up(n_generic + (size_t)h[4 * c + MJX_CLS_G], 32);
+    }
     const size_t nchunks = (size_t)list_chunks(d->view.total_blocks);
     size_t       off = 0;
     const size_t off_chunks = off;
@@ -308,6 +316,11 @@ static int dropon_finish(mjx_ctx *ctx, mjx_dropon *d) {
     e = cudaMalloc(&d->slab2, d->slab2_bytes);
     if(e != cudaSuccess) return fail(ctx, e, "cudaMalloc(compiled dropon lists)");
     char *base = (char *)d->slab2;
+    if(n_generic) { // padding slots: entry 0xffffffff, A = Ds = 0
+        e = cudaMemsetAsync(base + off_lg, 0xff, n_generic * sizeof(uint32_t), ctx->stream);
+        if(e == cudaSuccess) e = cudaMemsetAsync(base + off_ds, 0, n_generic * 512, ctx->stream);
+        if(e != cudaSuccess) return fail(ctx, e, "clear generic list");
+    }
     d->view.list_simple = (const uint32_t *)(base + off_ls);
     d->view.list_generic = (const uint32_t *)(base + off_lg);
     d->view.n_simple = (int)n_simple;
@@ -472,6 +485,8 @@ int mjx_dropon_class_counts(mjx_ctx *ctx, const mjx_dropon *d, long long counts[
     for(int i = 0; i < 4; i++) counts[i] = d->counts[i];
     return MJX_OK;
 }
+
+int mjx_dropon_generic_slots(const mjx_dropon *d) { return d ? d->view.n_generic : 0; }
 
 int mjx_dropon_download_generic(mjx_ctx *ctx, const mjx_dropon *d, uint32_t *list, float *Ds, float *A) {
     int rv = use_device(ctx);

@@ -31,10 +31,10 @@ struct DropView {
     int             ncomp;
     int             total_blocks;
     const uint32_t *list_simple;  // OPAQUE and U blocks
-    const uint32_t *list_generic; // G blocks
-    int             n_simple, n_generic;
+    const uint32_t *list_generic; // G blocks; every component starts on a multiple of 32, gaps hold 0xffffffff
+    int             n_simple, n_generic; // n_generic counts slots (a multiple of 32), not blocks
     const float    *gDs; // [n_generic][64] overlay coefficients * IDCT prescale (natural order)
-    const float    *gA;  // [n_generic][64] pixel-domain alpha / 255 = IDCT2(W) / 255
+    const float    *gA;  // [n_generic][64] pixel-domain alpha / 255 = IDCT2(W) / 255, stored Q-paired: (8i + k)*2 + h = A[2i + h][k]
 };
 
 static inline __host__ __device__ uint32_t entry_pack(int comp, int row, int col) {
@@ -65,6 +65,7 @@ struct mjx_dropon {
     int16_t       *W[MJX_MAX_COMPONENTS] = {};
     uint32_t      *meta[MJX_MAX_COMPONENTS] = {};
     long long      counts[4] = {}; // blocks per class, all components
+    int            generic_pad[MJX_MAX_COMPONENTS] = {}; // padding slots before each component's part of the generic list
 };
 
 struct mjx_ctx {

@@ -68,6 +68,7 @@ MJX_HD int wrap16(int x) { return (int)(int16_t)(uint16_t)(uint32_t)x; }
 // (exhaustively checked in tests/test_host_emul.py).
 // ---------------------------------------------------------------------------------------
 MJX_HD float quant_rcp(int q) { return (1.0f / (float)q) * 1.000000476837158203125f; }
+MJX_HD float quant_rcp_f(float q) { return (1.0f / q) * 1.000000476837158203125f; } // q already converted
 
 MJX_HD int tdiv(int a, float rq) {
 #if defined(__CUDA_ARCH__)
@@ -127,6 +128,11 @@ MJX_HD int blend_uniform(int I, int D, int q, float rq, float w4) {
 
 MJX_HD float inv_scale(int k) {
     const float t[8] = MJX_INV_SCALE_INIT;
+    return t[k];
+}
+MJX_HD double fwd_scale_d(int k) { // the constants c_fwd2 in k2_compose.cu is built from
+    const double t[8] = {0.35355339059327376, 0.25489778955207959, 0.27059805007309851, 0.30067244346752264,
+                         0.35355339059327376, 0.44998811156820786, 0.65328148243818826, 1.28145772387075308};
     return t[k];
 }
 MJX_HD float fwd_scale(int k) {
@@ -306,6 +312,192 @@ MJX_HD uint32_t pack2_int16(float lo, float hi) {
 // Equal to tdiv(deq + (int)Y, rq) whenever no int16 wrap-around occurs (|deq + Y| < 32768),
 // which holds for every JPEG a conforming encoder produces; the strict kernel keeps the wraps.
 MJX_HD float requant_f(float deq_f, float Y, float rq) { return trunc_f((deq_f + trunc_f(Y)) * rq); }
+
+// ---------------------------------------------------------------------------------------
+// packed fp32 (sm_100a FADD2 / FMUL2 / FFMA2: two fp32 lanes per instruction, per-operand negate
+// and a broadcast scalar immediate are free).  The generic class runs entirely on these: one
+// thread owns one block as 32 pairs, so every 1-D pass is 30 packed instructions per pair of
+// rows / columns instead of 60 scalar ones.  Host versions (test aid) round identically.
+// ---------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+typedef float2 F2;
+#else
+struct F2 {
+    float x, y;
+};
+#endif
+MJX_HD F2 f2(float x, float y) {
+    F2 r;
+    r.x = x, r.y = y;
+    return r;
+}
+MJX_HD F2 neg2(F2 a) { return f2(-a.x, -a.y); }
+// a*b + c rounded toward zero in one step (host model): the product of two floats is exact in
+// double, and here |a*b| < 2^23 = |c| with equal signs, so truncating the product and adding c
+// lands on the float grid (spacing 1) exactly where the hardware's single RZ rounding does
+MJX_HD float fma_rz_magic(float a, float b, float c) {
+    const double p = (double)a * (double)b;
+    const double t = p < 0 ? ceil(p) : floor(p);
+    return (float)(t + (double)c);
+}
+#if defined(__CUDA_ARCH__)
+MJX_HD F2 add2(F2 a, F2 b) { return __fadd2_rn(a, b); }
+MJX_HD F2 sub2(F2 a, F2 b) { return __fadd2_rn(a, neg2(b)); }
+MJX_HD F2 mul2(F2 a, F2 b) { return __fmul2_rn(a, b); }
+MJX_HD F2 fma2(F2 a, F2 b, F2 c) { return __ffma2_rn(a, b, c); }
+MJX_HD F2 fma2_rz(F2 a, F2 b, F2 c) { return __ffma2_rz(a, b, c); }
+MJX_HD float add1(float a, float b) { return __fadd_rn(a, b); }
+MJX_HD float sub1(float a, float b) { return __fadd_rn(a, -b); }
+#else
+MJX_HD F2 add2(F2 a, F2 b) { return f2(a.x + b.x, a.y + b.y); }
+MJX_HD F2 sub2(F2 a, F2 b) { return f2(a.x - b.x, a.y - b.y); }
+MJX_HD F2 mul2(F2 a, F2 b) { return f2(a.x * b.x, a.y * b.y); }
+MJX_HD F2 fma2(F2 a, F2 b, F2 c) { return f2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+MJX_HD F2 fma2_rz(F2 a, F2 b, F2 c) { return f2(fma_rz_magic(a.x, b.x, c.x), fma_rz_magic(a.y, b.y, c.y)); }
+MJX_HD float add1(float a, float b) { return a + b; }
+MJX_HD float sub1(float a, float b) { return a - b; }
+#endif
+MJX_HD F2 bc2(float c) { return f2(c, c); }
+
+// 8-point AAN inverse DCT on pairs, elements v[0], v[S], .. v[7S].  If TO is non-null the last
+// butterfly stage is done with scalar adds that write the result in the OTHER pairing (see
+// k2_generic_kernel): the pair (.x, .y) of output element k goes to TO[..] halves chosen by the
+// caller through the two index maps below.  Plain form first.
+template <int S>
+MJX_HD void idct8p(F2 *v) {
+    F2 t10 = add2(v[0], v[4 * S]), t11 = sub2(v[0], v[4 * S]);
+    F2 t13 = add2(v[2 * S], v[6 * S]), t12 = fma2(sub2(v[2 * S], v[6 * S]), bc2(1.414213562373095049f), neg2(t13));
+    F2 t0 = add2(t10, t13), t3 = sub2(t10, t13), t1 = add2(t11, t12), t2 = sub2(t11, t12);
+    F2 z13 = add2(v[5 * S], v[3 * S]), z10 = sub2(v[5 * S], v[3 * S]), z11 = add2(v[S], v[7 * S]), z12 = sub2(v[S], v[7 * S]);
+    F2 t7 = add2(z11, z13);
+    F2 z5 = mul2(add2(z10, z12), bc2(1.847759065022573512f));
+    F2 t6 = sub2(fma2(z10, bc2(-2.613125929752753056f), z5), t7);
+    F2 t5 = fma2(sub2(z11, z13), bc2(1.414213562373095049f), neg2(t6));
+    F2 t4 = sub2(fma2(z12, bc2(-1.082392200292393968f), z5), t5);
+    v[0] = add2(t0, t7);
+    v[7 * S] = sub2(t0, t7);
+    v[S] = add2(t1, t6);
+    v[6 * S] = sub2(t1, t6);
+    v[2 * S] = add2(t2, t5);
+    v[5 * S] = sub2(t2, t5);
+    v[3 * S] = add2(t3, t4);
+    v[4 * S] = sub2(t3, t4);
+}
+
+// the same, for column pair j of a block held as P pairs  x[4r + j] = (row r, cols 2j, 2j+1);
+// the result is written as Q pairs  y[8i + k] = (rows 2i, 2i+1; col k)  by a scalar last stage
+MJX_HD void idct8p_cols_to_rowpairs(const F2 *x, F2 *y, int j) {
+    const F2 *v = x + j;
+    F2 t10 = add2(v[0], v[16]), t11 = sub2(v[0], v[16]);
+    F2 t13 = add2(v[8], v[24]), t12 = fma2(sub2(v[8], v[24]), bc2(1.414213562373095049f), neg2(t13));
+    F2 t0 = add2(t10, t13), t3 = sub2(t10, t13), t1 = add2(t11, t12), t2 = sub2(t11, t12);
+    F2 z13 = add2(v[20], v[12]), z10 = sub2(v[20], v[12]), z11 = add2(v[4], v[28]), z12 = sub2(v[4], v[28]);
+    F2 t7 = add2(z11, z13);
+    F2 z5 = mul2(add2(z10, z12), bc2(1.847759065022573512f));
+    F2 t6 = sub2(fma2(z10, bc2(-2.613125929752753056f), z5), t7);
+    F2 t5 = fma2(sub2(z11, z13), bc2(1.414213562373095049f), neg2(t6));
+    F2 t4 = sub2(fma2(z12, bc2(-1.082392200292393968f), z5), t5);
+    // rows 0..7 = t0+t7, t1+t6, t2+t5, t3+t4, t3-t4, t2-t5, t1-t6, t0-t7
+    y[0 + 2 * j] = f2(add1(t0.x, t7.x), add1(t1.x, t6.x));
+    y[0 + 2 * j + 1] = f2(add1(t0.y, t7.y), add1(t1.y, t6.y));
+    y[8 + 2 * j] = f2(add1(t2.x, t5.x), add1(t3.x, t4.x));
+    y[8 + 2 * j + 1] = f2(add1(t2.y, t5.y), add1(t3.y, t4.y));
+    y[16 + 2 * j] = f2(sub1(t3.x, t4.x), sub1(t2.x, t5.x));
+    y[16 + 2 * j + 1] = f2(sub1(t3.y, t4.y), sub1(t2.y, t5.y));
+    y[24 + 2 * j] = f2(sub1(t1.x, t6.x), sub1(t0.x, t7.x));
+    y[24 + 2 * j + 1] = f2(sub1(t1.y, t6.y), sub1(t0.y, t7.y));
+}
+
+template <int S>
+MJX_HD void fdct8p(F2 *v) {
+    F2 t0 = add2(v[0], v[7 * S]), t7 = sub2(v[0], v[7 * S]), t1 = add2(v[S], v[6 * S]), t6 = sub2(v[S], v[6 * S]);
+    F2 t2 = add2(v[2 * S], v[5 * S]), t5 = sub2(v[2 * S], v[5 * S]), t3 = add2(v[3 * S], v[4 * S]), t4 = sub2(v[3 * S], v[4 * S]);
+    F2 t10 = add2(t0, t3), t13 = sub2(t0, t3), t11 = add2(t1, t2), t12 = sub2(t1, t2);
+    v[0] = add2(t10, t11);
+    v[4 * S] = sub2(t10, t11);
+    F2 z1 = mul2(add2(t12, t13), bc2(0.707106781186547524f));
+    v[2 * S] = add2(t13, z1);
+    v[6 * S] = sub2(t13, z1);
+    t10 = add2(t4, t5);
+    t11 = add2(t5, t6);
+    t12 = add2(t6, t7);
+    F2 z5 = mul2(sub2(t10, t12), bc2(0.382683432365089772f));
+    F2 z2 = fma2(t10, bc2(0.541196100146196985f), z5);
+    F2 z4 = fma2(t12, bc2(1.306562964876376527f), z5);
+    F2 z11 = fma2(t11, bc2(0.707106781186547524f), t7), z13 = fma2(t11, bc2(-0.707106781186547524f), t7);
+    v[5 * S] = add2(z13, z2);
+    v[3 * S] = sub2(z13, z2);
+    v[S] = add2(z11, z4);
+    v[7 * S] = sub2(z11, z4);
+}
+
+// forward transform of row pair i held as Q pairs y[8i + k]; the result is written as P pairs
+// x[4r + j] = (row r, cols 2j, 2j+1) by a scalar last stage
+MJX_HD void fdct8p_rowpairs_to_cols(const F2 *y, F2 *x, int i) {
+    const F2 *v = y + 8 * i;
+    F2 t0 = add2(v[0], v[7]), t7 = sub2(v[0], v[7]), t1 = add2(v[1], v[6]), t6 = sub2(v[1], v[6]);
+    F2 t2 = add2(v[2], v[5]), t5 = sub2(v[2], v[5]), t3 = add2(v[3], v[4]), t4 = sub2(v[3], v[4]);
+    F2 t10 = add2(t0, t3), t13 = sub2(t0, t3), t11 = add2(t1, t2), t12 = sub2(t1, t2);
+    F2 z1 = mul2(add2(t12, t13), bc2(0.707106781186547524f));
+    F2 u10 = add2(t4, t5), u11 = add2(t5, t6), u12 = add2(t6, t7);
+    F2 z5 = mul2(sub2(u10, u12), bc2(0.382683432365089772f));
+    F2 z2 = fma2(u10, bc2(0.541196100146196985f), z5);
+    F2 z4 = fma2(u12, bc2(1.306562964876376527f), z5);
+    F2 z11 = fma2(u11, bc2(0.707106781186547524f), t7), z13 = fma2(u11, bc2(-0.707106781186547524f), t7);
+    // cols 0..7 = t10+t11, z11+z4, t13+z1, z13-z2, t10-t11, z13+z2, t13-z1, z11-z4
+    F2 *lo = x + 4 * (2 * i), *hi = x + 4 * (2 * i + 1);
+    lo[0] = f2(add1(t10.x, t11.x), add1(z11.x, z4.x));
+    hi[0] = f2(add1(t10.y, t11.y), add1(z11.y, z4.y));
+    lo[1] = f2(add1(t13.x, z1.x), sub1(z13.x, z2.x));
+    hi[1] = f2(add1(t13.y, z1.y), sub1(z13.y, z2.y));
+    lo[2] = f2(sub1(t10.x, t11.x), add1(z13.x, z2.x));
+    hi[2] = f2(sub1(t10.y, t11.y), add1(z13.y, z2.y));
+    lo[3] = f2(sub1(t13.x, z1.x), sub1(z11.x, z4.x));
+    hi[3] = f2(sub1(t13.y, z1.y), sub1(z11.y, z4.y));
+}
+
+// +-2^23 with the sign of v: the magic addend that makes a round-toward-zero add truncate
+MJX_HD float signed_magic(float v) {
+    uint32_t u;
+#if defined(__CUDA_ARCH__)
+    u = __float_as_uint(v);
+#else
+    memcpy(&u, &v, 4);
+#endif
+    u = (u & 0x80000000u) | 0x4B000000u;
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+#endif
+}
+MJX_HD F2 signed_magic2(F2 v) { return f2(signed_magic(v.x), signed_magic(v.y)); }
+
+// one pair of generic coefficients, fp32 pipe only:
+//   t   = trunc(y * f)                       (the reference's (int)Y, src/compose.c:315-324)
+//   a   = I*q + t                            (dequantised + blend term; exact, integers < 2^24)
+//   out = trunc(a / q) as int16 bits         (src/compose.c:327-336)
+// trunc(y*f) comes from ONE round-toward-zero FMA onto +-2^23, trunc(a/q) from one onto the biased
+// reciprocal (quant_rcp, exact for |a| < 2^20, tests/test_host_emul.py); the int16 bit pattern is
+// the low half of (value + 1.5*2^23).  Returns the two int16 packed in one word.
+MJX_HD uint32_t requant_pair(F2 y, F2 f, F2 I, F2 q, F2 rq) {
+    const F2 sm = signed_magic2(y);
+    const F2 t = sub2(fma2_rz(y, f, sm), sm);
+    const F2 a = fma2(I, q, t);
+    const F2 sa = signed_magic2(a);
+    const F2 m = fma2_rz(a, rq, sa);
+    const F2 o = add2(m, sub2(bc2(12582912.0f), sa));
+    uint32_t lo, hi;
+#if defined(__CUDA_ARCH__)
+    lo = __float_as_uint(o.x), hi = __float_as_uint(o.y);
+    return __byte_perm(lo, hi, 0x5410);
+#else
+    memcpy(&lo, &o.x, 4), memcpy(&hi, &o.y, 4);
+    return (lo & 0xffffu) | (hi << 16);
+#endif
+}
 
 // libjpeg-turbo jccolor.c RGB -> YCbCr, 16-bit fixed point
 MJX_HD int rgb_to_y(int r, int g, int b) { return (19595 * r + 38470 * g + 7471 * b + 32768) >> 16; }

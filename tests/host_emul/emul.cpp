@@ -88,34 +88,61 @@ int emul_compose_block(int16_t *I, const int16_t *D, const int16_t *W, const uin
     return (int)cls;
 }
 
-// the generic class as the thread-per-block kernel computes it (k2 generic kernel): float tables
-// qs = q*s, qf = q, rq; dropon side Ds = D*s and pixel-domain alpha A = IDCT2(W*s/255); fp32-pipe
-// requantisation without int<->float conversions.
+// the generic class exactly as k2_generic_kernel computes it: float tables qs = q*s, q, rq per
+// image; dropon side Ds = D*s and pixel-domain alpha A = IDCT2(W*s/255) (k1_lists.cu); packed
+// arithmetic in the two pairings P (row r; cols 2j, 2j+1) and Q (rows 2i, 2i+1; col k);
+// requant_pair() for the fp32-pipe requantisation.
 void emul_generic_block_v2(int16_t *I, const int16_t *D, const int16_t *W, const uint16_t *q) {
-    float x[64], A[64], deq[64];
+    float A[8][8];
+    F2    x[32], y[32];
     for(int v = 0; v < 8; v++)
-        for(int u = 0; u < 8; u++) {
-            const int   i = 8 * v + u;
-            const float s = inv_scale(v) * inv_scale(u);
-            const float Ds = (float)D[i] * s, qs = (float)q[i] * s, qf = (float)q[i];
-            A[i] = (float)W[i] * (s * (1.0f / 255.0f));
-            deq[i] = (float)I[i] * qf;
-            x[i] = Ds - (float)I[i] * qs;
+        for(int u = 0; u < 8; u++) A[v][u] = (float)W[8 * v + u] * ((inv_scale(v) * inv_scale(u)) * (1.0f / 255.0f));
+    for(int v = 0; v < 8; v++) idct8(A[v]);
+    transpose(A);
+    for(int v = 0; v < 8; v++) idct8(A[v]);
+    transpose(A); // natural [py][px]
+    for(int r = 0; r < 8; r++)
+        for(int j = 0; j < 4; j++) {
+            F2 Ip, qs, ds;
+            float *Ipp = &Ip.x, *qsp = &qs.x, *dsp = &ds.x;
+            for(int h = 0; h < 2; h++) {
+                const int   i = 8 * r + 2 * j + h;
+                const float s = inv_scale(r) * inv_scale(2 * j + h);
+                Ipp[h] = (float)I[i];
+                qsp[h] = (float)q[i] * s;
+                dsp[h] = (float)D[i] * s;
+            }
+            x[4 * r + j] = fma2(Ip, neg2(qs), ds);
         }
-    for(int v = 0; v < 8; v++) idct8s<1>(A + 8 * v), idct8s<1>(x + 8 * v);
-    for(int u = 0; u < 8; u++) idct8s<8>(A + u), idct8s<8>(x + u);
-    for(int i = 0; i < 64; i++) x[i] *= A[i];
-    for(int u = 0; u < 8; u++) fdct8s<8>(x + u);
-    for(int v = 0; v < 8; v++) fdct8s<1>(x + 8 * v);
-    for(int v = 0; v < 8; v++)
-        for(int u = 0; u < 8; u += 2) {
-            const int   i = 8 * v + u;
-            const float o0 = requant_f(deq[i], x[i] * (fwd_scale(v) * fwd_scale(u)), quant_rcp(q[i]));
-            const float o1 = requant_f(deq[i + 1], x[i + 1] * (fwd_scale(v) * fwd_scale(u + 1)), quant_rcp(q[i + 1]));
-            const uint32_t pk = pack2_int16(o0, o1);
+    for(int j = 0; j < 4; j++) idct8p_cols_to_rowpairs(x, y, j);
+    for(int i = 0; i < 4; i++) idct8p<1>(y + 8 * i);
+    for(int i = 0; i < 4; i++)
+        for(int k = 0; k < 8; k++) y[8 * i + k] = mul2(y[8 * i + k], f2(A[2 * i][k], A[2 * i + 1][k]));
+    for(int i = 0; i < 4; i++) fdct8p_rowpairs_to_cols(y, x, i);
+    for(int j = 0; j < 4; j++) fdct8p<4>(x + j);
+    for(int r = 0; r < 8; r++)
+        for(int j = 0; j < 4; j++) {
+            const int      i = 8 * r + 2 * j;
+            const F2       f = f2((float)((double)fwd_scale_d(r) * fwd_scale_d(2 * j)), (float)((double)fwd_scale_d(r) * fwd_scale_d(2 * j + 1)));
+            const uint32_t pk = requant_pair(x[4 * r + j], f, f2((float)I[i], (float)I[i + 1]), f2((float)q[i], (float)q[i + 1]),
+                                             f2(quant_rcp_f((float)q[i]), quant_rcp_f((float)q[i + 1])));
             I[i] = (int16_t)(pk & 0xffffu);
             I[i + 1] = (int16_t)(pk >> 16);
         }
+}
+
+// exhaustive check of the requantisation's truncating division: low int16 of requant_pair with
+// y = 0 must equal a / q for a = I*q + 0 ... covered through emul_requant_check below
+long long emul_requant_check(int q, int amin, int amax) {
+    long long   bad = 0;
+    const float rq = quant_rcp_f((float)q);
+    for(int a = amin; a <= amax; a++) {
+        // a = I*q + t with I = 0: feed t through y (f = 1): t = trunc(y) = a
+        const uint32_t pk = requant_pair(f2((float)a + (a < 0 ? -0.25f : 0.25f), (float)a), f2(1.0f, 1.0f), f2(0.0f, 0.0f), f2((float)q, (float)q), f2(rq, rq));
+        const int      want = a / q;
+        if((int16_t)(pk & 0xffffu) != (int16_t)want || (int16_t)(pk >> 16) != (int16_t)want) bad++;
+    }
+    return bad;
 }
 
 void emul_compose_plane(int16_t *plane, int stride_blocks, int x0, int y0, const int16_t *Dp, const int16_t *Wp, int wb,

@@ -22,6 +22,7 @@ def emul(built):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.dirname(hdr), src, "-o", SO])
     E = C.CDLL(SO)
     E.emul_tdiv_check.restype = C.c_longlong
+    E.emul_requant_check.restype = C.c_longlong
     return E
 
 
@@ -32,7 +33,16 @@ def test_tdiv_reciprocal_is_exact(emul):
         assert emul.emul_tdiv_check(lo, lo + 60) == 0
 
 
-def test_k2_arithmetic_vs_oracle(emul, built, port):
+def test_requant_pair_division_is_exact(emul):
+    # the fp32-pipe requantisation of the generic class: trunc(a / q) for every dequantised value the
+    # fast path can see (|a| <= 2^17 covers int16 products plus any blend term), 8-bit and 16-bit tables
+    for q in list(range(1, 256)) + [256, 1000, 4095, 20000, 65535]:
+        assert emul.emul_requant_check(q, -(1 << 17), 1 << 17) == 0, q
+
+
+@pytest.mark.parametrize("v2", [0, 1])
+def test_k2_arithmetic_vs_oracle(emul, built, port, v2):
+    emul.emul_set_generic_v2(v2)
     from libmodjpeg_b200 import Jpeg
     from oracle import oracle_py as O
 
