@@ -33,6 +33,8 @@
 //
 // Roofline: HBM.  Algorithmic bytes per block: T 0, OPAQUE 128 (write), U/G 256 (read + write),
 // plus the compiled dropon once per launch (L2 / shared-memory resident across the images).
+#include <stdlib.h>
+
 #include "mjx_device.cuh"
 
 namespace mjx {
@@ -247,31 +249,30 @@ __global__ void __launch_bounds__(kThreads) k2_simple_kernel(const FastParams p)
 // scalar adds per pass instead of a register transpose.  ~1.4 k issue slots per block (the
 // scalar fp32 version needed ~2.3 k), which moves the class from issue-bound to HBM-bound.
 
-static constexpr int kGWarps = 4;
-static constexpr int kGThreads = kGWarps * 32;
 static constexpr int kGStages = 2;
-static constexpr int kInBytes = 32 * 128;  // one image's 32 blocks
-static constexpr int kQRawBytes = 128;     // its quantisation table as stored (64 x uint16)
-static constexpr int kAddrBytes = 32 * 8;  // global addresses of the 32 blocks
+// Shared-memory blocks are PADDED by one 16-byte chunk (stride 144 B for int16 blocks, 272 B for
+// float blocks): lane t reading chunk c of "its" block t hits bank group (t + c) mod 8, so the
+// thread-per-block 128-bit accesses are conflict-free AND every address is lane base + immediate
+// (an XOR swizzle costs a LOP3 + IADD per access: ~100 issue slots per block).
+static constexpr int kInStride = 144, kF32Stride = 272;
+static constexpr int kInBytes = 32 * kInStride; // one image's 32 blocks
+static constexpr int kQRawBytes = 128;          // its quantisation table as stored (64 x uint16)
+static constexpr int kAddrBytes = 32 * 8;       // global addresses of the 32 blocks
 static constexpr int kStageBytes = kInBytes + kQRawBytes + kAddrBytes;
 static constexpr int kTabBytes = 3 * 64 * 4; // q * prescale, q, biased 1/q as floats (current image)
 static constexpr int kWarpBytes = kGStages * kStageBytes + kTabBytes;
-static constexpr int kTileBytes = 2 * 32 * 256; // A (Q-paired) and Ds of the tile
-static constexpr int kGSmem = kTileBytes + kGWarps * kWarpBytes;
+static constexpr int kTileHalf = 32 * kF32Stride; // A (Q-paired) or Ds of the tile
+static constexpr int kTileBytes = 2 * kTileHalf;
+static constexpr int g_smem(int warps) { return kTileBytes + warps * kWarpBytes; }
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(unsigned dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+// 16 bytes global -> shared; nbytes == 0 zero-fills without touching `src` (no branch for absent blocks)
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src, unsigned nbytes = 16u) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// 16-byte chunk `c` of block `t` inside a buffer whose blocks are B bytes: XOR swizzle so that the
-// 8 threads of a quarter-warp, reading the same chunk of 8 consecutive blocks, hit 8 distinct
-// bank groups (the layout TMA calls SWIZZLE_128B)
-template <int B>
-__device__ __forceinline__ int swz(int t, int c) { return t * B + ((c ^ (t & 7)) << 4); }
 
 // sign-extend with PRMT, convert with the full-rate I2FP.F32.S32 (the compiler's I2F.S16 issues at 1/4 rate)
 // (PTX prmt replicates the sign of a byte when bit 3 of its selector nibble is set; the
@@ -299,11 +300,14 @@ static __constant__ FwdScale2 c_fwd2 = {{
 #undef MJX_F
 }};
 
-__global__ void __launch_bounds__(kGThreads, 3) k2_generic_kernel(const FastParams p) {
+template <int kGWarps, int kMinCtas>
+__global__ void __launch_bounds__(kGWarps * 32, kMinCtas) k2_generic_kernel(const FastParams p) {
+    constexpr int kGThreads = kGWarps * 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_item;
     const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char *tileA = smem_raw, *tileD = smem_raw + kTileBytes / 2;
+    // per-lane bases; everything below is base + immediate
+    const unsigned char *myA = smem_raw + lane * kF32Stride, *myD = smem_raw + kTileHalf + lane * kF32Stride;
     unsigned char *ws = smem_raw + kTileBytes + warp * kWarpBytes;
     float         *tab = reinterpret_cast<float *>(ws + kGStages * kStageBytes);
     const unsigned ws32 = smem_u32(ws), tile32 = smem_u32(smem_raw);
@@ -338,11 +342,12 @@ __global__ void __launch_bounds__(kGThreads, 3) k2_generic_kernel(const FastPara
             }
             tile_c = __shfl_sync(0xffffffffu, my_c, 0); // entry 0 of a tile is always a real block
             const float *ga = p.drop.gA + (size_t)tile * 32 * 64, *gd = p.drop.gDs + (size_t)tile * 32 * 64;
+            // 512 chunks of 16 B per array; thread -> chunk (tid & 15) of blocks (tid >> 4) + 8j
+            const unsigned tdst = tile32 + (threadIdx.x >> 4) * kF32Stride + (threadIdx.x & 15) * 16;
 #pragma unroll
-            for(int j = 0; j < 4; j++) {
-                const int g = j * kGThreads + threadIdx.x, t = g >> 4, c = g & 15;
-                cp_async16(tile32 + swz<256>(t, c), ga + g * 4);
-                cp_async16(tile32 + kTileBytes / 2 + swz<256>(t, c), gd + g * 4);
+            for(int j = 0; j < 512 / kGThreads; j++) {
+                cp_async16(tdst + j * (kGThreads / 16) * kF32Stride, ga + (j * kGThreads + threadIdx.x) * 4);
+                cp_async16(tdst + kTileHalf + j * (kGThreads / 16) * kF32Stride, gd + (j * kGThreads + threadIdx.x) * 4);
             }
         }
 
@@ -358,14 +363,16 @@ __global__ void __launch_bounds__(kGThreads, 3) k2_generic_kernel(const FastPara
                 a = im.plane[my_c] + ((unsigned long long)my_row * im.stride_blocks[my_c] + my_col) * 128ull;
             addr[lane] = a;
             __syncwarp();
-            const unsigned sb32 = ws32 + st * kStageBytes;
+            // lane -> chunk (lane & 7) of blocks (lane >> 3) + 4j
+            const unsigned            dst = ws32 + st * kStageBytes + (lane >> 3) * kInStride + (lane & 7) * 16;
+            const unsigned long long *ap = addr + (lane >> 3);
+            const unsigned            coff = (lane & 7) * 16;
 #pragma unroll
             for(int j = 0; j < 8; j++) {
-                const int                g = j * 32 + lane, t = g >> 3, c = g & 7;
-                const unsigned long long b = addr[t];
-                if(b) cp_async16(sb32 + swz<128>(t, c), reinterpret_cast<const void *>(b + c * 16));
+                const unsigned long long b = ap[4 * j];
+                cp_async16(dst + j * 4 * kInStride, reinterpret_cast<const void *>((b ? b : (unsigned long long)(uintptr_t)p.items) + coff), b ? 16u : 0u);
             }
-            if(lane < 8) cp_async16(sb32 + kInBytes + lane * 16, reinterpret_cast<const char *>(&im.q[tile_c][0]) + lane * 16);
+            if(lane < 8) cp_async16(ws32 + st * kStageBytes + kInBytes + lane * 16, reinterpret_cast<const char *>(&im.q[tile_c][0]) + lane * 16);
         };
 
         if(i0 < i1) prefetch(i0, 0);
@@ -382,7 +389,7 @@ __global__ void __launch_bounds__(kGThreads, 3) k2_generic_kernel(const FastPara
             __syncwarp();
 
             unsigned char            *sb = ws + st * kStageBytes;
-            unsigned char            *in = sb;
+            unsigned char            *my_in = sb + lane * kInStride;
             const unsigned long long *addr = reinterpret_cast<const unsigned long long *>(sb + kInBytes + kQRawBytes);
             {   // float tables of this image: entries 2*lane, 2*lane + 1
                 const uint32_t qw = *reinterpret_cast<const uint32_t *>(sb + kInBytes + lane * 4);
@@ -397,9 +404,9 @@ __global__ void __launch_bounds__(kGThreads, 3) k2_generic_kernel(const FastPara
                 F2 x[32], y[32];
 #pragma unroll
                 for(int r = 0; r < 8; r++) {
-                    const uint4  w = *reinterpret_cast<const uint4 *>(in + swz<128>(lane, r));
-                    const float4 d0 = *reinterpret_cast<const float4 *>(tileD + swz<256>(lane, 2 * r));
-                    const float4 d1 = *reinterpret_cast<const float4 *>(tileD + swz<256>(lane, 2 * r + 1));
+                    const uint4  w = *reinterpret_cast<const uint4 *>(my_in + r * 16);
+                    const float4 d0 = *reinterpret_cast<const float4 *>(myD + r * 32);
+                    const float4 d1 = *reinterpret_cast<const float4 *>(myD + r * 32 + 16);
                     const float4 s0 = *reinterpret_cast<const float4 *>(tab + r * 8);
                     const float4 s1 = *reinterpret_cast<const float4 *>(tab + r * 8 + 4);
                     // (D - I*q) * prescale
@@ -414,7 +421,7 @@ __global__ void __launch_bounds__(kGThreads, 3) k2_generic_kernel(const FastPara
                 for(int i = 0; i < 4; i++) idct8p<1>(y + 8 * i);
 #pragma unroll
                 for(int c = 0; c < 16; c++) {
-                    const float4 a = *reinterpret_cast<const float4 *>(tileA + swz<256>(lane, c));
+                    const float4 a = *reinterpret_cast<const float4 *>(myA + c * 16);
                     y[2 * c] = mul2(y[2 * c], f2(a.x, a.y));
                     y[2 * c + 1] = mul2(y[2 * c + 1], f2(a.z, a.w));
                 }
@@ -424,7 +431,7 @@ __global__ void __launch_bounds__(kGThreads, 3) k2_generic_kernel(const FastPara
                 for(int j = 0; j < 4; j++) fdct8p<4>(x + j);
 #pragma unroll
                 for(int r = 0; r < 8; r++) {
-                    const uint4  w = *reinterpret_cast<const uint4 *>(in + swz<128>(lane, r));
+                    const uint4  w = *reinterpret_cast<const uint4 *>(my_in + r * 16);
                     const float4 q0 = *reinterpret_cast<const float4 *>(tab + 64 + r * 8);
                     const float4 q1 = *reinterpret_cast<const float4 *>(tab + 64 + r * 8 + 4);
                     const float4 r0 = *reinterpret_cast<const float4 *>(tab + 128 + r * 8);
@@ -434,18 +441,20 @@ __global__ void __launch_bounds__(kGThreads, 3) k2_generic_kernel(const FastPara
                     o.y = requant_pair(x[4 * r + 1], c_fwd2.v[4 * r + 1], s16pair(w.y), f2(q0.z, q0.w), f2(r0.z, r0.w));
                     o.z = requant_pair(x[4 * r + 2], c_fwd2.v[4 * r + 2], s16pair(w.z), f2(q1.x, q1.y), f2(r1.x, r1.y));
                     o.w = requant_pair(x[4 * r + 3], c_fwd2.v[4 * r + 3], s16pair(w.w), f2(q1.z, q1.w), f2(r1.z, r1.w));
-                    *reinterpret_cast<uint4 *>(in + swz<128>(lane, r)) = o;
+                    *reinterpret_cast<uint4 *>(my_in + r * 16) = o;
                 }
             }
             __syncwarp();
-            // coalesced write-back: 8 lanes per block
+            // coalesced write-back: 8 lanes per block, lane -> chunk (lane & 7) of blocks (lane >> 3) + 4j
+            {
+                const unsigned char      *src = sb + (lane >> 3) * kInStride + (lane & 7) * 16;
+                const unsigned long long *ap = addr + (lane >> 3);
+                const unsigned            coff = (lane & 7) * 16;
 #pragma unroll
-            for(int j = 0; j < 8; j++) {
-                const int                g = j * 32 + lane, t = g >> 3, c = g & 7;
-                const unsigned long long b = addr[t];
-                if(b) {
-                    const uint4 v = *reinterpret_cast<const uint4 *>(in + swz<128>(t, c));
-                    __stcs(reinterpret_cast<uint4 *>(b + c * 16), v);
+                for(int j = 0; j < 8; j++) {
+                    const unsigned long long b = ap[4 * j];
+                    const uint4              v = *reinterpret_cast<const uint4 *>(src + j * 4 * kInStride);
+                    if(b) __stcs(reinterpret_cast<uint4 *>(b + coff), v);
                 }
             }
             __syncwarp();
@@ -481,11 +490,16 @@ cudaError_t launch_k2(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, 
     }
     if(view.n_simple == 0 && view.n_generic == 0) return cudaSuccess;
 
-    static int ctas_per_sm = 0; // idempotent; a benign race at worst computes it twice
+    // CTA shape of the generic kernel: 4 warps x 3 CTAs/SM (default) or 8 warps x 2 CTAs/SM (MJX_K2_WARPS=8)
+    static int  ctas_per_sm = 0, g_warps = 4; // idempotent; a benign race at worst computes them twice
+    static void (*g_kernel)(const FastParams) = nullptr;
     if(ctas_per_sm == 0) {
-        if((e = cudaFuncSetAttribute(k2_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmem)) != cudaSuccess) return e;
+        const char *env = getenv("MJX_K2_WARPS");
+        g_warps = (env && atoi(env) == 8) ? 8 : 4;
+        g_kernel = g_warps == 8 ? k2_generic_kernel<8, 2> : k2_generic_kernel<4, 3>;
+        if((e = cudaFuncSetAttribute(g_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem(g_warps))) != cudaSuccess) return e;
         int occ = 0;
-        if((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_generic_kernel, kGThreads, kGSmem)) != cudaSuccess) return e;
+        if((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, g_kernel, g_warps * 32, g_smem(g_warps))) != cudaSuccess) return e;
         ctas_per_sm = occ > 0 ? occ : 1;
     }
     for(int first = 0; first < n; first += 65535) {
@@ -500,7 +514,7 @@ cudaError_t launch_k2(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, 
         p.n = cnt;
         p.block_x = block_x;
         p.block_y = block_y;
-        p.images_per_item = cnt < 32 ? cnt : 32;
+        p.images_per_item = cnt < 8 * g_warps ? cnt : 8 * g_warps;
 
         k2_tables_kernel<<<dim3((unsigned)cnt, (unsigned)view.ncomp), 64, 0, s>>>(p.items, view.ncomp, tables);
         if((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -517,7 +531,7 @@ cudaError_t launch_k2(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, 
             const int nitems = ntiles * ((cnt + p.images_per_item - 1) / p.images_per_item);
             const int sms = sm_count > 0 ? sm_count : 148;
             const int ctas = nitems < sms * ctas_per_sm ? nitems : sms * ctas_per_sm;
-            k2_generic_kernel<<<ctas, kGThreads, kGSmem, s>>>(p);
+            g_kernel<<<ctas, g_warps * 32, g_smem(g_warps), s>>>(p);
             if((e = cudaGetLastError()) != cudaSuccess) return e;
             if(launches) (*launches)++;
         }
