@@ -340,7 +340,10 @@ __global__ void __launch_bounds__(kGWarps * 32, kMinCtas) k2_generic_kernel(cons
                 my_row = p.block_y * dc.vs + entry_row(e);
                 my_col = p.block_x * dc.hs + entry_col(e);
             }
-            tile_c = __shfl_sync(0xffffffffu, my_c, 0); // entry 0 of a tile is always a real block
+            tile_c = 0; // tiles hold one component only (the list is padded per component)
+#pragma unroll
+            for(int c = 1; c < MJX_MAX_COMPONENTS; c++)
+                if(c < p.drop.ncomp && tile >= p.drop.gtile_start[c]) tile_c = c;
             const float *ga = p.drop.gA + (size_t)tile * 32 * 64, *gd = p.drop.gDs + (size_t)tile * 32 * 64;
             // 512 chunks of 16 B per array; thread -> chunk (tid & 15) of blocks (tid >> 4) + 8j
             const unsigned tdst = tile32 + (threadIdx.x >> 4) * kF32Stride + (threadIdx.x & 15) * 16;
@@ -354,28 +357,42 @@ __global__ void __launch_bounds__(kGWarps * 32, kMinCtas) k2_generic_kernel(cons
         const int i0 = chunk * p.images_per_item + warp, i1 = min(p.n, (chunk + 1) * p.images_per_item);
 
         // issue the loads of image `img` into stage `st` (addresses of the 32 blocks first)
-        auto prefetch = [&](int img, int st) {
-            const mjx_image_desc_t &im = p.items[img];
-            unsigned char          *sb = ws + st * kStageBytes;
-            unsigned long long     *addr = reinterpret_cast<unsigned long long *>(sb + kInBytes + kQRawBytes);
-            unsigned long long      a = 0;
-            if(my_valid && my_row < im.rows[my_c] && my_col < im.stride_blocks[my_c])
-                a = im.plane[my_c] + ((unsigned long long)my_row * im.stride_blocks[my_c] + my_col) * 128ull;
+        // this warp's images of the item are i0 + k * kGWarps: lane k fetches image k's plane pointer,
+        // stride and height once per item; the per-image values are then broadcast by shuffle, so no
+        // global load sits on the per-image path
+        unsigned long long d_plane = 0;
+        int                d_stride = 0, d_rows = 0;
+        if(i0 + lane * kGWarps < i1) {
+            const mjx_image_desc_t &im = p.items[i0 + lane * kGWarps];
+            d_plane = im.plane[tile_c];
+            d_stride = im.stride_blocks[tile_c];
+            d_rows = im.rows[tile_c];
+        }
+
+        // issue the loads of the warp's k-th image into stage `st` (addresses of the 32 blocks first)
+        auto prefetch = [&](int k, int st) {
+            const unsigned long long plane = __shfl_sync(0xffffffffu, d_plane, k);
+            const int                stride = __shfl_sync(0xffffffffu, d_stride, k), rows = __shfl_sync(0xffffffffu, d_rows, k);
+            unsigned char           *sb = ws + st * kStageBytes;
+            unsigned long long      *addr = reinterpret_cast<unsigned long long *>(sb + kInBytes + kQRawBytes);
+            unsigned long long       a = 0;
+            if(my_valid && my_row < rows && my_col < stride) a = plane + ((unsigned long long)my_row * stride + my_col) * 128ull;
             addr[lane] = a;
             __syncwarp();
             // lane -> chunk (lane & 7) of blocks (lane >> 3) + 4j
             const unsigned            dst = ws32 + st * kStageBytes + (lane >> 3) * kInStride + (lane & 7) * 16;
             const unsigned long long *ap = addr + (lane >> 3);
             const unsigned            coff = (lane & 7) * 16;
+            unsigned long long        b[8];
 #pragma unroll
-            for(int j = 0; j < 8; j++) {
-                const unsigned long long b = ap[4 * j];
-                cp_async16(dst + j * 4 * kInStride, reinterpret_cast<const void *>((b ? b : (unsigned long long)(uintptr_t)p.items) + coff), b ? 16u : 0u);
-            }
-            if(lane < 8) cp_async16(ws32 + st * kStageBytes + kInBytes + lane * 16, reinterpret_cast<const char *>(&im.q[tile_c][0]) + lane * 16);
+            for(int j = 0; j < 8; j++) b[j] = ap[4 * j];
+#pragma unroll
+            for(int j = 0; j < 8; j++)
+                cp_async16(dst + j * 4 * kInStride, reinterpret_cast<const void *>((b[j] ? b[j] : (unsigned long long)(uintptr_t)p.items) + coff), b[j] ? 16u : 0u);
+            if(lane < 8) cp_async16(ws32 + st * kStageBytes + kInBytes + lane * 16, reinterpret_cast<const char *>(&p.items[i0 + k * kGWarps].q[tile_c][0]) + lane * 16);
         };
 
-        if(i0 < i1) prefetch(i0, 0);
+        if(i0 < i1) prefetch(0, 0);
         cp_async_commit();
         if(new_tile) {
             cp_async_wait<0>();
@@ -383,7 +400,7 @@ __global__ void __launch_bounds__(kGWarps * 32, kMinCtas) k2_generic_kernel(cons
         }
         for(int img = i0, it = 0; img < i1; img += kGWarps, it++) {
             const int st = it & 1;
-            if(img + kGWarps < i1) prefetch(img + kGWarps, st ^ 1);
+            if(img + kGWarps < i1) prefetch(it + 1, st ^ 1);
             cp_async_commit();
             cp_async_wait<1>(); // everything but the newest group: image `img` has landed
             __syncwarp();
@@ -451,11 +468,16 @@ __global__ void __launch_bounds__(kGWarps * 32, kMinCtas) k2_generic_kernel(cons
                 const unsigned long long *ap = addr + (lane >> 3);
                 const unsigned            coff = (lane & 7) * 16;
 #pragma unroll
+                unsigned long long b[8];
+                uint4              v[8];
+#pragma unroll
                 for(int j = 0; j < 8; j++) {
-                    const unsigned long long b = ap[4 * j];
-                    const uint4              v = *reinterpret_cast<const uint4 *>(src + j * 4 * kInStride);
-                    if(b) __stcs(reinterpret_cast<uint4 *>(b + coff), v);
+                    b[j] = ap[4 * j];
+                    v[j] = *reinterpret_cast<const uint4 *>(src + j * 4 * kInStride);
                 }
+#pragma unroll
+                for(int j = 0; j < 8; j++)
+                    if(b[j]) __stcs(reinterpret_cast<uint4 *>(b[j] + coff), v[j]);
             }
             __syncwarp();
         }
@@ -514,7 +536,7 @@ cudaError_t launch_k2(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, 
         p.n = cnt;
         p.block_x = block_x;
         p.block_y = block_y;
-        p.images_per_item = cnt < 8 * g_warps ? cnt : 8 * g_warps;
+        p.images_per_item = cnt < 16 * g_warps ? cnt : 16 * g_warps; // <= 32 per warp (one descriptor per lane)
 
         k2_tables_kernel<<<dim3((unsigned)cnt, (unsigned)view.ncomp), 64, 0, s>>>(p.items, view.ncomp, tables);
         if((e = cudaGetLastError()) != cudaSuccess) return e;

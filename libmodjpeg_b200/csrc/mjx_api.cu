@@ -297,6 +297,7 @@ static int dropon_finish(mjx_ctx *ctx, mjx_dropon *d) {
         for(int i = 0; i < 4; i++) d->counts[i] += (long long)h[4 * c + i];
         n_simple += (size_t)(h[4 * c + MJX_CLS_U] + h[4 * c + MJX_CLS_OPAQUE]);
         d->generic_pad[c] = (int)(n_generic - g_blocks);
+        d->view.gtile_start[c] = (int)(n_generic / 32);
         g_blocks += (size_t)h[4 * c + MJX_CLS_G];
         n_generic = align_up(n_generic + (size_t)h[4 * c + MJX_CLS_G], 32);
     }

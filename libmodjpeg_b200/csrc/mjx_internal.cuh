@@ -33,6 +33,7 @@ struct DropView {
     const uint32_t *list_simple;  // OPAQUE and U blocks
     const uint32_t *list_generic; // G blocks; every component starts on a multiple of 32, gaps hold 0xffffffff
     int             n_simple, n_generic; // n_generic counts slots (a multiple of 32), not blocks
+    int             gtile_start[MJX_MAX_COMPONENTS]; // first tile (32 slots) of each component in list_generic
     const float    *gDs; // [n_generic][64] overlay coefficients * IDCT prescale (natural order)
     const float    *gA;  // [n_generic][64] pixel-domain alpha / 255 = IDCT2(W) / 255, stored Q-paired: (8i + k)*2 + h = A[2i + h][k]
 };
