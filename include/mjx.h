@@ -105,6 +105,9 @@ int         mjx_ctx_use_own_stream(mjx_ctx *ctx);                /* back to the 
 /* strict = 1: K2 runs as one kernel that reproduces the reference's int16 wrap-around on out-of-range
  * products (adversarial streams); default 0: the fast kernels, identical on every encoder-produced JPEG */
 int         mjx_ctx_set_strict(mjx_ctx *ctx, int strict);
+/* on = 1 (default): mjx_compose_batch_host runs K2 directly on page-locked (GPU-addressable) host planes, so only
+ * the blocks the dropon touches cross PCIe; 0: always stage the region under the dropon through device memory */
+int         mjx_ctx_set_zero_copy(mjx_ctx *ctx, int on);
 void       *mjx_ctx_stream(mjx_ctx *ctx);
 int         mjx_ctx_sync(mjx_ctx *ctx);
 const char *mjx_ctx_last_error(mjx_ctx *ctx);
@@ -154,7 +157,9 @@ int  mjx_dropon_class_counts(mjx_ctx *ctx, const mjx_dropon *d, long long counts
 /* n images resident in HBM, one compiled dropon at MCU position (block_x, block_y) on each */
 int mjx_compose_batch_device(mjx_ctx *ctx, const mjx_image_desc_t *items_dev, int n, const mjx_dropon *d,
                              int block_x, int block_y);
-/* n images in host memory: region under the dropon is staged H2D, blended, staged back */
+/* n images in host memory.  Page-locked planes (mjx_host_alloc / cudaHostRegister): one launch working directly on
+ * host memory (zero-copy, see mjx_ctx_set_zero_copy); pageable planes: the region under the dropon is staged H2D,
+ * blended and staged back through a 3-stream pipeline.  Returns when the host planes hold the result. */
 int mjx_compose_batch_host(mjx_ctx *ctx, const mjx_host_image_t *items, int n, const mjx_dropon *d,
                            int block_x, int block_y);
 /* one image given as libjpeg row pointers: rows[c][l] -> block (block_y*v_c + l, block_x*h_c) of component c,

@@ -127,6 +127,7 @@ def load_mjx() -> C.CDLL:
     L.mjx_dropon_class_counts.argtypes = [vp, vp, C.POINTER(C.c_longlong)]
     L.mjx_dropon_download_generic.argtypes = [vp, vp, vp, vp, vp]
     L.mjx_dropon_generic_slots.argtypes = [vp]
+    L.mjx_ctx_set_zero_copy.argtypes = [vp, C.c_int]
     L.mjx_compose_batch_device.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int]
     L.mjx_compose_batch_host.argtypes = [vp, C.POINTER(HostImage), C.c_int, vp, C.c_int, C.c_int]
     L.mjx_compose_rows_host.argtypes = [vp, C.c_int, vp, vp, vp]
@@ -235,6 +236,10 @@ class Engine:
             self._check(self.lib.mjx_ctx_use_own_stream(self.ctx), "mjx_ctx_use_own_stream")
         else:
             self._check(self.lib.mjx_ctx_set_stream(self.ctx, C.c_void_p(cuda_stream)), "mjx_ctx_set_stream")
+
+    def set_zero_copy(self, on: bool) -> None:
+        """on (default): compose_batch_host runs K2 directly on page-locked host planes; off: always stage"""
+        self._check(self.lib.mjx_ctx_set_zero_copy(self.ctx, 1 if on else 0), "mjx_ctx_set_zero_copy")
 
     def set_strict(self, strict: bool) -> None:
         """strict: one K2 kernel with the reference's int16 wrap-around (adversarial inputs); default fast kernels"""

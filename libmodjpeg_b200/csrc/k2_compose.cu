@@ -268,7 +268,7 @@ static constexpr int g_smem(int warps) { return kTileBytes + warps * kWarpBytes;
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 // 16 bytes global -> shared; nbytes == 0 zero-fills without touching `src` (no branch for absent blocks)
 __device__ __forceinline__ void cp_async16(unsigned dst, const void *src, unsigned nbytes = 16u) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>

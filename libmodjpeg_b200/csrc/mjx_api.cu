@@ -502,6 +502,12 @@ int mjx_dropon_download_generic(mjx_ctx *ctx, const mjx_dropon *d, uint32_t *lis
     return MJX_OK;
 }
 
+int mjx_ctx_set_zero_copy(mjx_ctx *ctx, int on) {
+    if(!ctx) return MJX_ERR_ARG;
+    ctx->zero_copy = on ? 1 : 0;
+    return MJX_OK;
+}
+
 int mjx_ctx_set_strict(mjx_ctx *ctx, int strict) {
     if(!ctx) return MJX_ERR_ARG;
     ctx->strict = strict ? 1 : 0;
@@ -595,7 +601,50 @@ int mjx_compose_batch_host(mjx_ctx *ctx, const mjx_host_image_t *items, int n, c
             if(block_x * dc.hs + dc.wb > items[i].stride_blocks[c] || block_y * dc.vs + dc.hb > items[i].rows[c])
                 return MJX_ERR_ARG;
         }
-    // per pipeline slot: one image's region in device memory; descriptors for all images in pinned memory
+    // Zero-copy path: when every plane lies in page-locked host memory the GPU can address (mjx_host_alloc,
+    // cudaHostAlloc, cudaHostRegister), K2 runs directly on the host planes in ONE launch over the whole batch:
+    // only the blocks the dropon touches cross PCIe (class G blocks are read and written, OPAQUE blocks are
+    // written only, transparent blocks and everything outside the dropon never move).
+    if(ctx->zero_copy) {
+        bool mapped = true;
+        for(int i = 0; i < n && mapped; i++)
+            for(int c = 0; c < ncomp && mapped; c++) {
+                cudaPointerAttributes at;
+                if(cudaPointerGetAttributes(&at, items[i].plane[c]) != cudaSuccess) {
+                    cudaGetLastError();
+                    mapped = false;
+                }
+                else mapped = (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged) && at.devicePointer != nullptr;
+            }
+        if(mapped) {
+            const size_t dbytes = sizeof(mjx_image_desc_t) * (size_t)n;
+            if((rv = ensure_pin(ctx, dbytes)) || (rv = ensure_desc(ctx, dbytes)) ||
+               (rv = ensure_scratch(ctx, k2_scratch_bytes(n < 65535 ? n : 65535, ncomp))))
+                return rv;
+            mjx_image_desc_t *desc = (mjx_image_desc_t *)ctx->pin;
+            memset(desc, 0, dbytes);
+            for(int i = 0; i < n; i++)
+                for(int c = 0; c < ncomp; c++) {
+                    cudaPointerAttributes at;
+                    MJX_CUDA(ctx, cudaPointerGetAttributes(&at, items[i].plane[c]));
+                    desc[i].plane[c] = (uint64_t)(uintptr_t)at.devicePointer;
+                    desc[i].stride_blocks[c] = items[i].stride_blocks[c];
+                    desc[i].rows[c] = items[i].rows[c];
+                    desc[i].wreal[c] = items[i].wreal[c];
+                    desc[i].hreal[c] = items[i].hreal[c];
+                    memcpy(desc[i].q[c], items[i].q[c], 128);
+                }
+            MJX_CUDA(ctx, cudaMemcpyAsync(ctx->desc_dev, desc, dbytes, cudaMemcpyHostToDevice, ctx->stream));
+            int         launches = 0;
+            cudaError_t e = launch_k2(ctx->stream, (const mjx_image_desc_t *)ctx->desc_dev, n, d->view, block_x, block_y, ctx->scratch,
+                                      ctx->strict, ctx->sm_count, &launches);
+            ctx->launches += launches;
+            if(e != cudaSuccess) return fail(ctx, e, "k2_compose_kernel");
+            MJX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            return MJX_OK;
+        }
+    }
+    // staged path -- per pipeline slot: one image's region in device memory; descriptors for all images in pinned memory
     size_t off[MJX_MAX_COMPONENTS], slot = 0;
     for(int c = 0; c < ncomp; c++) {
         off[c] = slot;

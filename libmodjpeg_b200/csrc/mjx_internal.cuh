@@ -77,6 +77,7 @@ struct mjx_ctx {
     long long    launches = 0;
     int          sm_count = 0;
     int          strict = 0; // 1: one kernel for every class with the reference's int16 wrap-around
+    int          zero_copy = 1; // batch-host calls on page-locked planes run K2 directly on host memory
 
     // staging pools for the host-pointer entry points (grown on demand, reused across calls)
     void  *pin = nullptr;

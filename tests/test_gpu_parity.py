@@ -216,6 +216,68 @@ def test_batch_host_equals_batch_device(engine):
     batch.free()
 
 
+def test_batch_host_zero_copy_equals_staged(engine):
+    """page-locked planes take the zero-copy path (K2 works on host memory, one launch for the batch);
+    it must give exactly what the staged path gives, and leave every block outside the dropon alone"""
+    from libmodjpeg_b200 import Layout, capi
+
+    dec = [_decode(util.jpeg_bytes(200, 136, "420", 85, seed=80 + i)) for i in range(5)]
+    info, samp = dec[0][1], dec[0][2]
+    raw = util.logo_rgba(128, 96, 64, 27)
+    i3, a3, scs, blend = util.ingest_raw(raw, 2, 255)
+    g = capi.geometry(info["width"], info["height"], 16, 16, 128, 96, 16, 5, 3)
+    cd = engine.dropon_compile(i3, a3, scs, Layout.make(3, samp), (g["blockoffset_x"], g["blockoffset_y"]),
+                               (g["crop_x"], g["crop_y"], g["crop_w"], g["crop_h"]))
+    staged = [[p.copy() for p in d[3]] for d in dec]
+    items = (capi.HostImage * len(dec))()
+    keep = []
+    for i, d in enumerate(dec):
+        items[i], k = capi.make_host_image(staged[i], d[4])
+        keep.append(k)
+    engine.compose_batch_host(items, len(dec), cd, g["block_x"], g["block_y"])  # pageable numpy memory: staged
+
+    sizes = [p.nbytes for p in dec[0][3]]
+    per_image = sum(sizes)
+    pinned = engine.host_alloc(per_image * len(dec))
+    zitems = (capi.HostImage * len(dec))()
+    views = []
+    for i, d in enumerate(dec):
+        off = i * per_image
+        vs = []
+        for c, p in enumerate(d[3]):
+            v = pinned[off:off + p.nbytes].view(np.int16).reshape(p.shape)
+            v[...] = p
+            vs.append(v)
+            off += p.nbytes
+        zitems[i], k = capi.make_host_image(vs, d[4])
+        keep.append(k)
+        views.append(vs)
+    l0 = engine.kernel_launches
+    engine.compose_batch_host(zitems, len(dec), cd, g["block_x"], g["block_y"])
+    assert engine.kernel_launches - l0 <= 3, "zero-copy path is one K2 launch sequence for the whole batch"
+    changed = 0
+    for i in range(len(dec)):
+        for a, b, before in zip(views[i], staged[i], dec[i][3]):
+            assert np.array_equal(a, b)
+            changed += int((a != before).sum())
+    assert changed > 0
+    engine.set_zero_copy(False)
+    try:
+        for i, d in enumerate(dec):
+            for v, p in zip(views[i], d[3]):
+                v[...] = p
+        l0 = engine.kernel_launches
+        engine.compose_batch_host(zitems, len(dec), cd, g["block_x"], g["block_y"])
+        assert engine.kernel_launches - l0 >= len(dec)  # staged: per-image launches
+        for i in range(len(dec)):
+            for a, b in zip(views[i], staged[i]):
+                assert np.array_equal(a, b)
+    finally:
+        engine.set_zero_copy(True)
+    engine.host_free(pinned)
+    cd.free()
+
+
 # ---------------------------------------------------------------------------------------------
 # the public API end to end: mj_compose / mj_effect_* of libmodjpeg.so
 # ---------------------------------------------------------------------------------------------
