@@ -108,6 +108,8 @@ int         mjx_ctx_set_strict(mjx_ctx *ctx, int strict);
 /* on = 1 (default): mjx_compose_batch_host runs K2 directly on page-locked (GPU-addressable) host planes, so only
  * the blocks the dropon touches cross PCIe; 0: always stage the region under the dropon through device memory */
 int         mjx_ctx_set_zero_copy(mjx_ctx *ctx, int on);
+/* profiling aid: which fast-path K2 kernels run -- bit 0 the OPAQUE/U kernel, bit 1 the G kernel (default 3 = both) */
+int         mjx_ctx_set_class_mask(mjx_ctx *ctx, int mask);
 void       *mjx_ctx_stream(mjx_ctx *ctx);
 int         mjx_ctx_sync(mjx_ctx *ctx);
 const char *mjx_ctx_last_error(mjx_ctx *ctx);

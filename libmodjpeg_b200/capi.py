@@ -128,6 +128,7 @@ def load_mjx() -> C.CDLL:
     L.mjx_dropon_download_generic.argtypes = [vp, vp, vp, vp, vp]
     L.mjx_dropon_generic_slots.argtypes = [vp]
     L.mjx_ctx_set_zero_copy.argtypes = [vp, C.c_int]
+    L.mjx_ctx_set_class_mask.argtypes = [vp, C.c_int]
     L.mjx_compose_batch_device.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int]
     L.mjx_compose_batch_host.argtypes = [vp, C.POINTER(HostImage), C.c_int, vp, C.c_int, C.c_int]
     L.mjx_compose_rows_host.argtypes = [vp, C.c_int, vp, vp, vp]
@@ -240,6 +241,10 @@ class Engine:
     def set_zero_copy(self, on: bool) -> None:
         """on (default): compose_batch_host runs K2 directly on page-locked host planes; off: always stage"""
         self._check(self.lib.mjx_ctx_set_zero_copy(self.ctx, 1 if on else 0), "mjx_ctx_set_zero_copy")
+
+    def set_class_mask(self, mask: int) -> None:
+        """profiling aid: bit 0 = OPAQUE/U kernel, bit 1 = G kernel of the fast K2 path (default 3)"""
+        self._check(self.lib.mjx_ctx_set_class_mask(self.ctx, mask), "mjx_ctx_set_class_mask")
 
     def set_strict(self, strict: bool) -> None:
         """strict: one K2 kernel with the reference's int16 wrap-around (adversarial inputs); default fast kernels"""

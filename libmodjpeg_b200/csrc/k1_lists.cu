@@ -17,7 +17,8 @@ struct ListParams {
     const uint32_t *meta[MJX_MAX_COMPONENTS];
     int             wb[MJX_MAX_COMPONENTS];
     int             start[MJX_MAX_COMPONENTS];
-    int             pad[MJX_MAX_COMPONENTS]; // slots inserted before component c's entries in the generic list
+    int             pad[MJX_MAX_COMPONENTS];  // slots inserted before component c's entries in the generic list
+    int             spad[MJX_MAX_COMPONENTS]; // ... in the simple list
     int             ncomp, total_blocks;
 };
 
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(kChunk) list_fill_kernel(const ListParams p, c
     }
     __syncthreads();
     const unsigned below = (1u << lane) - 1u;
-    if(kind == 1) list_simple[chunk_offsets[2 * blockIdx.x] + warp_s[warp] + __popc(bs & below)] = e;
+    if(kind == 1) list_simple[chunk_offsets[2 * blockIdx.x] + warp_s[warp] + __popc(bs & below) + p.spad[entry_comp(e)]] = e;
     if(kind == 2) list_generic[chunk_offsets[2 * blockIdx.x + 1] + warp_g[warp] + __popc(bg & below) + p.pad[entry_comp(e)]] = e;
 }
 
@@ -137,6 +138,7 @@ cudaError_t launch_build_lists(cudaStream_t s, mjx_dropon *d, uint32_t *chunk_co
         p.wb[c] = d->view.comp[c].wb > 0 ? d->view.comp[c].wb : 1;
         p.start[c] = d->view.comp[c].start;
         p.pad[c] = d->generic_pad[c];
+        p.spad[c] = d->simple_pad[c];
     }
     cudaError_t e;
     list_count_kernel<<<nchunks, kChunk, 0, s>>>(p, chunk_counts_dev);

@@ -292,14 +292,19 @@ static int dropon_finish(mjx_ctx *ctx, mjx_dropon *d) {
     if(e != cudaSuccess) return fail(ctx, e, "count classes");
     for(int i = 0; i < 4; i++) d->counts[i] = 0;
     // the generic list is padded so that every component starts on a tile (32-entry) boundary
-    size_t n_simple = 0, n_generic = 0, g_blocks = 0;
+    // both lists are padded so that every component starts on a tile (32-entry) boundary
+    size_t n_simple = 0, n_generic = 0, s_blocks = 0, g_blocks = 0;
     for(int c = 0; c < d->view.ncomp; c++) {
         for(int i = 0; i < 4; i++) d->counts[i] += (long long)h[4 * c + i];
-        n_simple += (size_t)(h[4 * c + MJX_CLS_U] + h[4 * c + MJX_CLS_OPAQUE]);
+        const size_t ns = (size_t)(h[4 * c + MJX_CLS_U] + h[4 * c + MJX_CLS_OPAQUE]), ng = (size_t)h[4 * c + MJX_CLS_G];
+        d->simple_pad[c] = (int)(n_simple - s_blocks);
+        d->view.stile_start[c] = (int)(n_simple / 32);
+        s_blocks += ns;
+        n_simple = align_up(n_simple + ns, 32);
         d->generic_pad[c] = (int)(n_generic - g_blocks);
         d->view.gtile_start[c] = (int)(n_generic / 32);
-        g_blocks += (size_t)h[4 * c + MJX_CLS_G];
-        n_generic = align_up(n_generic + (size_t)h[4 * c + MJX_CLS_G], 32);
+        g_blocks += ng;
+        n_generic = align_up(n_generic + ng, 32);
     }
     const size_t nchunks = (size_t)list_chunks(d->view.total_blocks);
     size_t       off = 0;
@@ -321,6 +326,10 @@ static int dropon_finish(mjx_ctx *ctx, mjx_dropon *d) {
         e = cudaMemsetAsync(base + off_lg, 0xff, n_generic * sizeof(uint32_t), ctx->stream);
         if(e == cudaSuccess) e = cudaMemsetAsync(base + off_ds, 0, n_generic * 512, ctx->stream);
         if(e != cudaSuccess) return fail(ctx, e, "clear generic list");
+    }
+    if(n_simple) {
+        e = cudaMemsetAsync(base + off_ls, 0xff, n_simple * sizeof(uint32_t), ctx->stream);
+        if(e != cudaSuccess) return fail(ctx, e, "clear simple list");
     }
     d->view.list_simple = (const uint32_t *)(base + off_ls);
     d->view.list_generic = (const uint32_t *)(base + off_lg);
@@ -502,6 +511,12 @@ int mjx_dropon_download_generic(mjx_ctx *ctx, const mjx_dropon *d, uint32_t *lis
     return MJX_OK;
 }
 
+int mjx_ctx_set_class_mask(mjx_ctx *ctx, int mask) {
+    if(!ctx) return MJX_ERR_ARG;
+    ctx->class_mask = mask & 3;
+    return MJX_OK;
+}
+
 int mjx_ctx_set_zero_copy(mjx_ctx *ctx, int on) {
     if(!ctx) return MJX_ERR_ARG;
     ctx->zero_copy = on ? 1 : 0;
@@ -524,9 +539,9 @@ int mjx_compose_batch_device(mjx_ctx *ctx, const mjx_image_desc_t *items_dev, in
     if(rv) return rv;
     if(!items_dev || !d || n < 0 || block_x < 0 || block_y < 0) return MJX_ERR_ARG;
     if(d->device != ctx->device) return MJX_ERR_ARG;
-    if((rv = ensure_scratch(ctx, k2_scratch_bytes(n < 65535 ? n : 65535, d->view.ncomp))) != MJX_OK) return rv;
+    if((rv = ensure_scratch(ctx, k2_scratch_bytes())) != MJX_OK) return rv;
     int         launches = 0;
-    cudaError_t e = launch_k2(ctx->stream, items_dev, n, d->view, block_x, block_y, ctx->scratch, ctx->strict, ctx->sm_count, &launches);
+    cudaError_t e = launch_k2(ctx->stream, items_dev, n, d->view, block_x, block_y, ctx->scratch, ctx->strict, ctx->sm_count, ctx->class_mask, &launches);
     ctx->launches += launches;
     if(e != cudaSuccess) return fail(ctx, e, "k2_compose_kernel");
     return MJX_OK;
@@ -564,9 +579,9 @@ int mjx_compose_rows_host(mjx_ctx *ctx, int ncomp, int16_t *const *const *rows, 
     }
     MJX_CUDA(ctx, cudaMemcpyAsync(dev, pin, total, cudaMemcpyHostToDevice, ctx->stream));
     // the staged region starts at the dropon's origin: MCU position (0, 0)
-    if((rv = ensure_scratch(ctx, k2_scratch_bytes(1, ncomp))) != MJX_OK) return rv;
+    if((rv = ensure_scratch(ctx, k2_scratch_bytes())) != MJX_OK) return rv;
     int         launches = 0;
-    cudaError_t e = launch_k2(ctx->stream, (const mjx_image_desc_t *)dev, 1, d->view, 0, 0, ctx->scratch, ctx->strict, ctx->sm_count, &launches);
+    cudaError_t e = launch_k2(ctx->stream, (const mjx_image_desc_t *)dev, 1, d->view, 0, 0, ctx->scratch, ctx->strict, ctx->sm_count, ctx->class_mask, &launches);
     ctx->launches += launches;
     if(e != cudaSuccess) return fail(ctx, e, "k2_compose_kernel");
     const size_t head = align_up(sizeof(mjx_image_desc_t), 256);
@@ -619,7 +634,7 @@ int mjx_compose_batch_host(mjx_ctx *ctx, const mjx_host_image_t *items, int n, c
         if(mapped) {
             const size_t dbytes = sizeof(mjx_image_desc_t) * (size_t)n;
             if((rv = ensure_pin(ctx, dbytes)) || (rv = ensure_desc(ctx, dbytes)) ||
-               (rv = ensure_scratch(ctx, k2_scratch_bytes(n < 65535 ? n : 65535, ncomp))))
+               (rv = ensure_scratch(ctx, k2_scratch_bytes())))
                 return rv;
             mjx_image_desc_t *desc = (mjx_image_desc_t *)ctx->pin;
             memset(desc, 0, dbytes);
@@ -637,7 +652,7 @@ int mjx_compose_batch_host(mjx_ctx *ctx, const mjx_host_image_t *items, int n, c
             MJX_CUDA(ctx, cudaMemcpyAsync(ctx->desc_dev, desc, dbytes, cudaMemcpyHostToDevice, ctx->stream));
             int         launches = 0;
             cudaError_t e = launch_k2(ctx->stream, (const mjx_image_desc_t *)ctx->desc_dev, n, d->view, block_x, block_y, ctx->scratch,
-                                      ctx->strict, ctx->sm_count, &launches);
+                                      ctx->strict, ctx->sm_count, ctx->class_mask, &launches);
             ctx->launches += launches;
             if(e != cudaSuccess) return fail(ctx, e, "k2_compose_kernel");
             MJX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -652,7 +667,7 @@ int mjx_compose_batch_host(mjx_ctx *ctx, const mjx_host_image_t *items, int n, c
     }
     const int    P = mjx_ctx::kPipe;
     const size_t desc_sz = align_up(sizeof(mjx_image_desc_t), 256);
-    const size_t scr_sz = align_up(k2_scratch_bytes(1, ncomp), 256);
+    const size_t scr_sz = align_up(k2_scratch_bytes(), 256);
     if((rv = pipe_init(ctx)) || (rv = ensure_dev(ctx, slot * P)) || (rv = ensure_desc(ctx, desc_sz * P)) || (rv = ensure_scratch(ctx, scr_sz * P)) ||
        (rv = ensure_pin(ctx, desc_sz * (size_t)n)))
         return rv;
@@ -690,7 +705,7 @@ int mjx_compose_batch_host(mjx_ctx *ctx, const mjx_host_image_t *items, int n, c
         }
         int         launches = 0;
         cudaError_t e = launch_k2(st, (const mjx_image_desc_t *)(ddev + desc_sz * s), 1, d->view, 0, 0, (char *)ctx->scratch + scr_sz * s,
-                                  ctx->strict, ctx->sm_count, &launches);
+                                  ctx->strict, ctx->sm_count, ctx->class_mask, &launches);
         ctx->launches += launches;
         if(e != cudaSuccess) return fail(ctx, e, "k2_compose_kernel");
         for(int c = 0; c < ncomp; c++) {

@@ -30,10 +30,11 @@ struct DropView {
     DropComp        comp[MJX_MAX_COMPONENTS];
     int             ncomp;
     int             total_blocks;
-    const uint32_t *list_simple;  // OPAQUE and U blocks
+    const uint32_t *list_simple;  // OPAQUE and U blocks; padded per component like list_generic
     const uint32_t *list_generic; // G blocks; every component starts on a multiple of 32, gaps hold 0xffffffff
-    int             n_simple, n_generic; // n_generic counts slots (a multiple of 32), not blocks
+    int             n_simple, n_generic; // slots (multiples of 32), not blocks
     int             gtile_start[MJX_MAX_COMPONENTS]; // first tile (32 slots) of each component in list_generic
+    int             stile_start[MJX_MAX_COMPONENTS]; // ... in list_simple
     const float    *gDs; // [n_generic][64] overlay coefficients * IDCT prescale (natural order)
     const float    *gA;  // [n_generic][64] pixel-domain alpha / 255 = IDCT2(W) / 255, stored Q-paired: (8i + k)*2 + h = A[2i + h][k]
 };
@@ -44,12 +45,6 @@ static inline __host__ __device__ uint32_t entry_pack(int comp, int row, int col
 static inline __host__ __device__ int entry_comp(uint32_t e) { return (int)(e >> 30); }
 static inline __host__ __device__ int entry_row(uint32_t e) { return (int)((e >> 15) & 0x7fffu); }
 static inline __host__ __device__ int entry_col(uint32_t e) { return (int)(e & 0x7fffu); }
-
-// per (image, component) float tables K2 reads instead of converting q on the fly
-static const int kTabQf = 0;   // (float) q
-static const int kTabQs = 64;  // q * IDCT prescale
-static const int kTabRq = 128; // biased reciprocal, see quant_rcp()
-static const int kTabFloats = 192;
 
 } // namespace mjx
 
@@ -67,6 +62,7 @@ struct mjx_dropon {
     uint32_t      *meta[MJX_MAX_COMPONENTS] = {};
     long long      counts[4] = {}; // blocks per class, all components
     int            generic_pad[MJX_MAX_COMPONENTS] = {}; // padding slots before each component's part of the generic list
+    int            simple_pad[MJX_MAX_COMPONENTS] = {};  // ... of the simple list
 };
 
 struct mjx_ctx {
@@ -77,6 +73,7 @@ struct mjx_ctx {
     long long    launches = 0;
     int          sm_count = 0;
     int          strict = 0; // 1: one kernel for every class with the reference's int16 wrap-around
+    int          class_mask = 3; // fast path: bit 0 = OPAQUE/U kernel, bit 1 = G kernel (profiling aid, default both)
     int          zero_copy = 1; // batch-host calls on page-locked planes run K2 directly on host memory
 
     // staging pools for the host-pointer entry points (grown on demand, reused across calls)
@@ -86,7 +83,7 @@ struct mjx_ctx {
     size_t dev_bytes = 0;
     void  *desc_dev = nullptr; // device array of mjx_image_desc_t for staged launches
     size_t desc_bytes = 0;
-    void  *scratch = nullptr; // per-launch K2 scratch: float tables + work counters
+    void  *scratch = nullptr; // per-launch K2 scratch: work counters
     size_t scratch_bytes = 0;
 
     // extra streams for the pipelined batch-host path
@@ -102,8 +99,8 @@ int  ensure_dev(mjx_ctx *ctx, size_t bytes);
 int  ensure_desc(mjx_ctx *ctx, size_t bytes);
 int  ensure_scratch(mjx_ctx *ctx, size_t bytes);
 
-// bytes of scratch one K2 launch over n images needs
-size_t k2_scratch_bytes(int n, int ncomp);
+// bytes of scratch one K2 launch needs (the work counter)
+size_t k2_scratch_bytes();
 
 // kernel launchers (each returns a cudaError_t from the launch; *launches += kernels launched)
 cudaError_t launch_k1(cudaStream_t s, const uint8_t *image3, const uint8_t *alpha3, int dw, int dh, int dropon_cs,
@@ -114,7 +111,7 @@ cudaError_t launch_count_classes(cudaStream_t s, const mjx_dropon *d, unsigned l
 // after classification: fill the work lists and the compact generic-class arrays (slab2 allocated)
 cudaError_t launch_build_lists(cudaStream_t s, mjx_dropon *d, uint32_t *chunk_counts_dev, int *launches);
 cudaError_t launch_k2(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, const DropView &view, int block_x,
-                      int block_y, void *scratch, int strict, int sm_count, int *launches);
+                      int block_y, void *scratch, int strict, int sm_count, int class_mask, int *launches);
 cudaError_t launch_k3(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, int ncomp, const mjx_effect_op_t *ops,
                       int nops, int *launches);
 

@@ -346,6 +346,7 @@ MJX_HD F2 sub2(F2 a, F2 b) { return __fadd2_rn(a, neg2(b)); }
 MJX_HD F2 mul2(F2 a, F2 b) { return __fmul2_rn(a, b); }
 MJX_HD F2 fma2(F2 a, F2 b, F2 c) { return __ffma2_rn(a, b, c); }
 MJX_HD F2 fma2_rz(F2 a, F2 b, F2 c) { return __ffma2_rz(a, b, c); }
+MJX_HD F2 add2_rz(F2 a, F2 b) { return __fadd2_rz(a, b); }
 MJX_HD float add1(float a, float b) { return __fadd_rn(a, b); }
 MJX_HD float sub1(float a, float b) { return __fadd_rn(a, -b); }
 #else
@@ -354,6 +355,7 @@ MJX_HD F2 sub2(F2 a, F2 b) { return f2(a.x - b.x, a.y - b.y); }
 MJX_HD F2 mul2(F2 a, F2 b) { return f2(a.x * b.x, a.y * b.y); }
 MJX_HD F2 fma2(F2 a, F2 b, F2 c) { return f2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
 MJX_HD F2 fma2_rz(F2 a, F2 b, F2 c) { return f2(fma_rz_magic(a.x, b.x, c.x), fma_rz_magic(a.y, b.y, c.y)); }
+MJX_HD F2 add2_rz(F2 a, F2 b) { return f2(fma_rz_magic(a.x, 1.0f, b.x), fma_rz_magic(a.y, 1.0f, b.y)); } // b = +-2^23, sign of a
 MJX_HD float add1(float a, float b) { return a + b; }
 MJX_HD float sub1(float a, float b) { return a - b; }
 #endif
@@ -497,6 +499,33 @@ MJX_HD uint32_t requant_pair(F2 y, F2 f, F2 I, F2 q, F2 rq) {
     memcpy(&lo, &o.x, 4), memcpy(&hi, &o.y, 4);
     return (lo & 0xffffu) | (hi << 16);
 #endif
+}
+
+// trunc(a / q) of a pair as two packed int16 (second half of requant_pair)
+MJX_HD uint32_t tdiv_pair(F2 a, F2 rq) {
+    const F2 sa = signed_magic2(a);
+    const F2 m = fma2_rz(a, rq, sa);
+    const F2 o = add2(m, sub2(bc2(12582912.0f), sa));
+    uint32_t lo, hi;
+#if defined(__CUDA_ARCH__)
+    lo = __float_as_uint(o.x), hi = __float_as_uint(o.y);
+    return __byte_perm(lo, hi, 0x5410);
+#else
+    memcpy(&lo, &o.x, 4), memcpy(&hi, &o.y, 4);
+    return (lo & 0xffffu) | (hi << 16);
+#endif
+}
+
+// one pair of uniform-alpha coefficients in the fp32 pipe, bit-exact with the reference whenever
+// no int16 wrap-around occurs (src/compose.c:277-336 with the single non-zero weight w0):
+//   Iq = I*q (exact), X = D - Iq (exact), Y = fl(X * w4)  [== (float)(4 * (double)X * (double)w0)],
+//   a = Iq + trunc(Y), out = trunc(a / q)
+MJX_HD uint32_t uniform_pair(F2 I, F2 D, F2 q, F2 rq, float w4) {
+    const F2 Iq = mul2(I, q);
+    const F2 Y = mul2(sub2(D, Iq), bc2(w4));
+    const F2 sm = signed_magic2(Y);
+    const F2 t = sub2(add2_rz(Y, sm), sm);
+    return tdiv_pair(add2(Iq, t), rq);
 }
 
 // libjpeg-turbo jccolor.c RGB -> YCbCr, 16-bit fixed point

@@ -145,6 +145,27 @@ long long emul_requant_check(int q, int amin, int amax) {
     return bad;
 }
 
+// the fp32-pipe U / OPAQUE arithmetic of k2_fast_kernel (uniform_pair, tdiv_pair) against the integer
+// formulation blend_uniform() / tdiv() that the oracle tests pin; pseudo-random sweep, returns mismatches
+long long emul_uniform_pair_check(int q, int wdc, int n, unsigned seed) {
+    long long   bad = 0;
+    const float rq = quant_rcp(q), w4 = uniform_w4(wdc);
+    unsigned    s = seed * 2654435761u + 12345u;
+    for(int i = 0; i < n; i++) {
+        s = s * 1664525u + 1013904223u;
+        const int lim = 32767 / q;
+        const int I = (int)((s >> 8) % (unsigned)(2 * lim + 1)) - lim; // |I*q| <= 32767: no int16 wrap
+        s = s * 1664525u + 1013904223u;
+        const int D = (int)((s >> 8) % 16601u) - 8300;
+        const int want = blend_uniform(I, D, q, rq, w4);
+        const uint32_t pk = uniform_pair(f2((float)I, (float)I), f2((float)D, (float)D), f2((float)q, (float)q), f2(rq, rq), w4);
+        if((int16_t)(pk & 0xffffu) != (int16_t)want || (int16_t)(pk >> 16) != (int16_t)want) bad++;
+        const uint32_t po = tdiv_pair(f2((float)D, (float)D), f2(rq, rq));
+        if((int16_t)(po & 0xffffu) != (int16_t)(D / q)) bad++;
+    }
+    return bad;
+}
+
 void emul_compose_plane(int16_t *plane, int stride_blocks, int x0, int y0, const int16_t *Dp, const int16_t *Wp, int wb,
                         int hb, const uint16_t *q, long long *class_counts) {
     for(int l = 0; l < hb; l++)

@@ -23,6 +23,7 @@ def emul(built):
     E = C.CDLL(SO)
     E.emul_tdiv_check.restype = C.c_longlong
     E.emul_requant_check.restype = C.c_longlong
+    E.emul_uniform_pair_check.restype = C.c_longlong
     return E
 
 
@@ -38,6 +39,13 @@ def test_requant_pair_division_is_exact(emul):
     # fast path can see (|a| <= 2^17 covers int16 products plus any blend term), 8-bit and 16-bit tables
     for q in list(range(1, 256)) + [256, 1000, 4095, 20000, 65535]:
         assert emul.emul_requant_check(q, -(1 << 17), 1 << 17) == 0, q
+
+
+def test_uniform_pair_equals_integer_formula(emul):
+    # U / OPAQUE classes in the fp32 pipe == the integer formulation (which the oracle tests pin bit-exactly)
+    for q in (1, 2, 3, 5, 8, 16, 17, 40, 99, 255):
+        for wdc in (1, 8, 255, 1020, 1024, 2039, 2040):
+            assert emul.emul_uniform_pair_check(q, wdc, 20000, q * 4099 + wdc) == 0, (q, wdc)
 
 
 @pytest.mark.parametrize("v2", [0, 1])
