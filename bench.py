@@ -202,6 +202,29 @@ def run_reference_arm(args, rank: int, world: int):
 # ------------------------------------------------------------------------------------------
 
 
+ORIG_AFFINITY = None
+
+
+def bind_to_gpu_numa_node(device: int) -> None:
+    """Pin this rank's host threads (and so its first-touch page-locked buffers) to the CPUs NVML reports as
+    local to the GPU: the e2e path streams host memory over PCIe, which a remote NUMA node would throttle."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        global ORIG_AFFINITY
+        ORIG_AFFINITY = set(os.sched_getaffinity(0))
+        allowed = cpus & ORIG_AFFINITY
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            log(f"[gpu {device}] host threads bound to {len(allowed)} GPU-local CPUs")
+    except Exception as e:  # affinity is an optimisation, never a requirement
+        log(f"[gpu {device}] no NUMA binding ({type(e).__name__}: {e})")
+
+
 def run_b200_arm(args, rank: int, local_rank: int, world: int):
     import torch
 
@@ -215,11 +238,14 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        # keep stdout to the one JSON line: NCCL's version banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist_mod
 
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
 
+    bind_to_gpu_numa_node(local_rank)
     engine = M.Engine(local_rank)
     # torch is plumbing here: it owns the device memory and the stream the kernels are launched
     # on, so that torch.cuda.Event brackets exactly the engine's launches
@@ -383,6 +409,8 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
+            if ORIG_AFFINITY:
+                os.sched_setaffinity(0, ORIG_AFFINITY)  # the reference arm gets every host core
             threads = host_threads()
             arm = CpuArm(jpegs[:4], logo, threads)
             arm.step(1)
