@@ -355,6 +355,51 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
     ms_simple = time_masked(1) if counts["OPAQUE"] + counts["U"] else 0.0
     ms_generic = time_masked(2) if counts["G"] else 0.0
 
+    # ---- the other two kernels of the path, on the same resident batch (rank 0 reports) -----------
+    other = {}
+    if not args.no_other_kernels:
+        engine.set_stream(stream.cuda_stream)
+
+        def timed(fn, reps):
+            fn()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                fn()
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) / reps
+
+        # K1: the 1920x1080 RGBA logo compiled for the 4:2:0 YCbCr layout, pixels already in HBM
+        # (device time of k1_compile_kernel + the list/prepare kernels + the two small D2H count reads)
+        px = torch.from_numpy(np.concatenate([i3.reshape(-1), a3.reshape(-1)])).to(dev)
+        npx = i3.size
+
+        def k1():
+            c = engine.dropon_compile(None, None, M.CS_RGB, layout, (g["blockoffset_x"], g["blockoffset_y"]),
+                                      (g["crop_x"], g["crop_y"], g["crop_w"], g["crop_h"]),
+                                      device_pixels=(px.data_ptr(), px.data_ptr() + npx, logo.shape[1], logo.shape[0]))
+            c.free()
+
+        ms = timed(k1, 5)
+        k1_bytes = 2 * npx + blocks_per_image * 64 * 2 * 2  # two 3-byte pixel buffers read, D and W int16 written
+        other["k1_dropon_compile"] = {"ms": ms, "pixels": npx // 3, "algorithmic_bytes": k1_bytes,
+                                      "achieved_gbs": k1_bytes / (ms * 1e-3) / 1e9, "mpixels_per_s": npx / 3 / (ms * 1e-3) / 1e6,
+                                      "note": "whole mjx_dropon_compile call (K1 + list build + cudaMalloc/cudaFree + stream syncs); launch/sync-bound at this size"}
+        # K3 on every image of the batch: DC-only pipeline (luminance + tint) and a rewrite pipeline (pixelate all components)
+        yb = shapes[0][0] * shapes[0][1]
+        cb = shapes[1][0] * shapes[1][1]
+        ms = timed(lambda: engine.effects_batch_device(descs_dev.data_ptr(), n, 3, [(3, 0, 40), (3, 1, 30), (3, 2, -30)]), 5)
+        dc_blocks = n * (yb + 2 * cb)
+        other["k3_effects_dc_only"] = {"ms": ms, "ops": "luminance 40 + tint 30,-30 fused", "blocks": dc_blocks, "algorithmic_bytes": dc_blocks * 4,
+                                       "sector_bytes": dc_blocks * 64, "achieved_gbs_sector": dc_blocks * 64 / (ms * 1e-3) / 1e9,
+                                       "gblocks_per_s": dc_blocks / (ms * 1e-3) / 1e9,
+                                       "note": "2 B read + 2 B written per block; DRAM moves a 32 B sector each way"}
+        ms = timed(lambda: engine.effects_batch_device(descs_dev.data_ptr(), n, 3, [(2, 0, 0), (2, 1, 0), (2, 2, 0)]), 5)
+        other["k3_effects_pixelate"] = {"ms": ms, "blocks": dc_blocks, "algorithmic_bytes": dc_blocks * 130,
+                                        "achieved_gbs": dc_blocks * 130 / (ms * 1e-3) / 1e9, "gblocks_per_s": dc_blocks / (ms * 1e-3) / 1e9}
+
     # ---- e2e: host planes through mjx_compose_batch_host ----------------------------------------
     n_e2e = min(n, args.e2e_images)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -470,6 +515,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
                          "step": {"achieved": achieved, "frac": achieved / peak, "algorithmic_bytes": alg_bytes, "ms": launch_ms,
                                   "what": "whole K2 step = k2_simple_kernel + k2_generic_kernel back to back"},
                          "kernels": kernels},
+            "other_kernels": other,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_mbps, "unit": "Mblocks/s",
                     # zero-copy: only touched blocks cross PCIe (G read + written, OPAQUE/U written; U also read)
@@ -501,6 +547,7 @@ def main():
     ap.add_argument("--e2e-images", type=int, default=1250)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-kernels", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
