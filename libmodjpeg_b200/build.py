@@ -24,6 +24,7 @@ LIB = os.path.join(PKG, "lib")
 OBJ = os.path.join(LIB, "obj")
 INCLUDE = os.path.join(ROOT, "include")
 JPEG_INC = os.path.join(ROOT, "third_party", "jpeg62")
+PNG_INC = os.path.join(ROOT, "third_party", "png16")
 
 CUDA_SOURCES = ["mjx_api.cu", "k1_dropon.cu", "k1_lists.cu", "k2_compose.cu", "k3_effects.cu"]
 HOST_SOURCES = ["mj_jpegio.c", "mj_image.c", "mj_dropon.c", "mj_compose.c", "mj_effect.c", "mj_device.c"]
@@ -50,6 +51,15 @@ def jpeg_runtime() -> str:
     return cands[0]
 
 
+def png_runtime() -> str | None:
+    """The libpng16 shared object bundled with Pillow (None: build without PNG dropon support)."""
+    import PIL
+
+    d = os.path.join(os.path.dirname(os.path.dirname(PIL.__file__)), "pillow.libs")
+    cands = sorted(glob.glob(os.path.join(d, "libpng16-*.so.16*")))
+    return cands[0] if cands else None
+
+
 def _newer(target: str, deps: list[str]) -> bool:
     if not os.path.exists(target):
         return True
@@ -71,7 +81,7 @@ def _run(cmd: list[str], verbose: bool) -> None:
 def build(verbose: bool = False, force: bool = False, ptxas_verbose: bool = False) -> dict:
     os.makedirs(OBJ, exist_ok=True)
     headers = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h")) + \
-        glob.glob(os.path.join(CSRC, "host", "*.h")) + glob.glob(os.path.join(JPEG_INC, "*.h")) + [__file__]
+        glob.glob(os.path.join(CSRC, "host", "*.h")) + glob.glob(os.path.join(JPEG_INC, "*.h")) + glob.glob(os.path.join(PNG_INC, "*.h")) + [__file__]
     nvcc = _nvcc()
 
     # ---- libmjx.so -------------------------------------------------------------------
@@ -97,6 +107,16 @@ def build(verbose: bool = False, force: bool = False, ptxas_verbose: bool = Fals
         if os.path.lexists(link):
             os.remove(link)
         os.symlink(jpeg_so, link)
+    png_so = png_runtime()
+    png_flags, png_link = [], []
+    if png_so:
+        plink = os.path.join(LIB, "libpng16.so")
+        if not os.path.islink(plink) or os.readlink(plink) != png_so:
+            if os.path.lexists(plink):
+                os.remove(plink)
+            os.symlink(png_so, plink)
+        png_flags = ["-DWITH_LIBPNG", "-I", PNG_INC]
+        png_link = ["-lpng16"]
     hobjs = []
     for src in HOST_SOURCES:
         s = os.path.join(CSRC, "host", src)
@@ -104,11 +124,11 @@ def build(verbose: bool = False, force: bool = False, ptxas_verbose: bool = Fals
         hobjs.append(o)
         if force or _newer(o, [s] + headers):
             _run(["gcc", "-std=gnu11", "-O2", "-Wall", "-Wextra", "-Wno-unused-parameter", "-Wno-clobbered", "-fPIC",
-                  "-I", INCLUDE, "-I", JPEG_INC, "-I", os.path.join(CSRC, "host"), "-c", s, "-o", o], verbose)
+                  "-I", INCLUDE, "-I", JPEG_INC, "-I", os.path.join(CSRC, "host")] + png_flags + ["-c", s, "-o", o], verbose)
     mj_so = os.path.join(LIB, "libmodjpeg.so")
     if force or _newer(mj_so, hobjs + [mjx_so]):
         _run(["gcc", "-shared", "-o", mj_so] + hobjs +
-             ["-L", LIB, "-lmjx", "-ljpeg", "-lpthread", "-lm",
+             ["-L", LIB, "-lmjx", "-ljpeg"] + png_link + ["-lpthread", "-lm",
               "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + os.path.dirname(jpeg_so),
               "-Wl,--version-script=" + os.path.join(CSRC, "host", "libmodjpeg.map")], verbose)
     return {"libmjx": mjx_so, "libmodjpeg": mj_so, "libjpeg": jpeg_so}

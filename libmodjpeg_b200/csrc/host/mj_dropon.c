@@ -10,6 +10,10 @@
 
 #include "mj_private.h"
 
+#ifdef WITH_LIBPNG
+#include <png.h>
+#endif
+
 void mj_init_dropon(mj_dropon_t *d) {
     if(d != NULL) memset(d, 0, sizeof(*d));
 }
@@ -111,13 +115,46 @@ static int dropon_from_jpeg(mj_dropon_t *d, const unsigned char *memory, size_t 
     return rv;
 }
 
+#ifdef WITH_LIBPNG
+/* PNG dropon through libpng's simplified API: always decoded to 8-bit RGBA, so the alpha channel (or
+ * tRNS) becomes the mask and blend is forced to MJ_BLEND_NONUNIFORM (role of reference src/dropon.c:163-201) */
+static int dropon_from_png(mj_dropon_t *d, const unsigned char *memory, size_t len) {
+    png_image image;
+    memset(&image, 0, sizeof(image));
+    image.version = PNG_IMAGE_VERSION;
+    if(png_image_begin_read_from_memory(&image, memory, len) == 0) return MJ_ERR_FILEIO;
+    if(image.width >= (2u << 16) || image.height >= (2u << 16)) {
+        png_image_free(&image);
+        return MJ_ERR_DROPON_DIMENSIONS;
+    }
+    image.format = PNG_FORMAT_RGBA;
+    unsigned char *rgba = (unsigned char *)malloc(PNG_IMAGE_SIZE(image) ? PNG_IMAGE_SIZE(image) : 1);
+    if(rgba == NULL) {
+        png_image_free(&image);
+        return MJ_ERR_MEMORY;
+    }
+    if(png_image_finish_read(&image, NULL, rgba, 0, NULL) == 0) {
+        free(rgba);
+        png_image_free(&image);
+        return MJ_ERR_FILEIO;
+    }
+    int rv = mj_read_dropon_from_raw(d, rgba, MJ_COLORSPACE_RGBA, (int)image.width, (int)image.height, MJ_BLEND_NONUNIFORM);
+    free(rgba);
+    png_image_free(&image);
+    return rv;
+}
+#endif
+
 int mj_read_dropon_from_memory(mj_dropon_t *d, const unsigned char *memory, size_t len, const unsigned char *maskmemory, size_t masklen, short blend) {
     if(d == NULL || memory == NULL || len < 8) return MJ_ERR_NULL_DATA;
     if(memory[0] == 0xFF && memory[1] == 0xD8 && memory[2] == 0xFF) /* JPEG SOI + marker */
         return dropon_from_jpeg(d, memory, len, maskmemory, masklen, blend);
-    /* PNG overlays: the reference reads them only when built WITH_LIBPNG (src/dropon.c:83-96);
-     * this build has no libpng headers, so like a reference built without it: unsupported.
-     * Decode the PNG to RGBA in the caller and use mj_read_dropon_from_raw. */
+#ifdef WITH_LIBPNG
+    if(memory[0] == 0x89 && memory[1] == 'P' && memory[2] == 'N' && memory[3] == 'G' && memory[4] == 0x0d && memory[5] == 0x0a &&
+       memory[6] == 0x1a && memory[7] == 0x0a)
+        return dropon_from_png(d, memory, len);
+#endif
+    /* anything else (and PNG when built without libpng, like the reference, src/dropon.c:80-96) */
     return MJ_ERR_UNSUPPORTED_FILETYPE;
 }
 

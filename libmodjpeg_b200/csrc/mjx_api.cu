@@ -81,6 +81,16 @@ int mjx_ctx_create(mjx_ctx **out, int device) {
     cudaError_t e = cudaSetDevice(device);
     if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if(e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if(e == cudaSuccess) {
+        // compiled dropons come from the device's stream-ordered pool; keep freed blocks cached so that the
+        // per-call compile of mj_compose (the reference recompiles per call too) never reaches the driver
+        cudaMemPool_t pool;
+        if(cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = 1ull << 30;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     if(e != cudaSuccess) {
         cudaGetLastError();
         delete ctx;
@@ -259,10 +269,10 @@ static int dropon_alloc(mjx_ctx *ctx, mjx_dropon **out, const mjx_layout_t *L, c
     d->view.ncomp = L->ncomp;
     d->view.total_blocks = start;
     d->slab_bytes = off ? off : 256;
-    cudaError_t e = cudaMalloc(&d->slab, d->slab_bytes);
+    cudaError_t e = cudaMallocAsync(&d->slab, d->slab_bytes, ctx->stream);
     if(e != cudaSuccess) {
         delete d;
-        return fail(ctx, e, "cudaMalloc(compiled dropon)");
+        return fail(ctx, e, "cudaMallocAsync(compiled dropon)");
     }
     for(int c = 0; c < L->ncomp; c++) {
         d->D[c] = (int16_t *)((char *)d->slab + offD[c]);
@@ -279,16 +289,16 @@ static int dropon_alloc(mjx_ctx *ctx, mjx_dropon **out, const mjx_layout_t *L, c
 // second half of a compile: read the class counts back, size and fill the work lists and the
 // compact generic-class arrays (k1_lists.cu).  Synchronises the stream (one-time per dropon).
 static int dropon_finish(mjx_ctx *ctx, mjx_dropon *d) {
-    const int           NC = MJX_MAX_COMPONENTS * 4;
-    unsigned long long *cnt_dev = nullptr;
-    MJX_CUDA(ctx, cudaMalloc(&cnt_dev, NC * sizeof(unsigned long long)));
-    cudaError_t e = cudaMemsetAsync(cnt_dev, 0, NC * sizeof(unsigned long long), ctx->stream);
+    const int NC = MJX_MAX_COMPONENTS * 4;
+    int       rvs = ensure_scratch(ctx, 256 + NC * sizeof(unsigned long long));
+    if(rvs) return rvs;
+    unsigned long long *cnt_dev = reinterpret_cast<unsigned long long *>((char *)ctx->scratch + 256); // after K2's work counter
+    cudaError_t         e = cudaMemsetAsync(cnt_dev, 0, NC * sizeof(unsigned long long), ctx->stream);
     if(e == cudaSuccess) e = launch_count_classes(ctx->stream, d, cnt_dev);
     ctx->launches += d->view.ncomp;
     unsigned long long h[MJX_MAX_COMPONENTS * 4] = {};
     if(e == cudaSuccess) e = cudaMemcpyAsync(h, cnt_dev, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
     if(e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(cnt_dev);
     if(e != cudaSuccess) return fail(ctx, e, "count classes");
     for(int i = 0; i < 4; i++) d->counts[i] = 0;
     // the generic list is padded so that every component starts on a tile (32-entry) boundary
@@ -319,8 +329,8 @@ static int dropon_finish(mjx_ctx *ctx, mjx_dropon *d) {
     const size_t off_a = off;
     off = align_up(off + n_generic * 256, 256);
     d->slab2_bytes = off ? off : 256;
-    e = cudaMalloc(&d->slab2, d->slab2_bytes);
-    if(e != cudaSuccess) return fail(ctx, e, "cudaMalloc(compiled dropon lists)");
+    e = cudaMallocAsync(&d->slab2, d->slab2_bytes, ctx->stream);
+    if(e != cudaSuccess) return fail(ctx, e, "cudaMallocAsync(compiled dropon lists)");
     char *base = (char *)d->slab2;
     if(n_generic) { // padding slots: entry 0xffffffff, A = Ds = 0
         e = cudaMemsetAsync(base + off_lg, 0xff, n_generic * sizeof(uint32_t), ctx->stream);
@@ -385,11 +395,11 @@ int mjx_dropon_compile(mjx_ctx *ctx, mjx_dropon **out, const uint8_t *image3, co
     void          *tmp = nullptr;
     const size_t   npx = (size_t)width * height * 3;
     if(!pixels_on_device) {
-        cudaError_t e = cudaMalloc(&tmp, 2 * npx);
+        cudaError_t e = cudaMallocAsync(&tmp, 2 * npx, ctx->stream);
         if(e == cudaSuccess) e = cudaMemcpyAsync(tmp, image3, npx, cudaMemcpyHostToDevice, ctx->stream);
         if(e == cudaSuccess) e = cudaMemcpyAsync((char *)tmp + npx, alpha3, npx, cudaMemcpyHostToDevice, ctx->stream);
         if(e != cudaSuccess) {
-            if(tmp) cudaFree(tmp);
+            if(tmp) cudaFreeAsync(tmp, ctx->stream);
             mjx_dropon_free(d);
             return fail(ctx, e, "upload dropon pixels");
         }
@@ -400,9 +410,9 @@ int mjx_dropon_compile(mjx_ctx *ctx, mjx_dropon **out, const uint8_t *image3, co
                               blockoffset_y, crop_x, crop_y, crop_w, crop_h, canvas_w, canvas_h, max_h, max_v, d);
     ctx->launches++;
     if(tmp) {
-        // the kernel reads tmp: free it only once the stream has drained
-        cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-        cudaFree(tmp);
+        // stream-ordered: released once the kernel that reads it has run.  The source pixels are pageable host
+        // memory, which cudaMemcpyAsync has already staged by the time it returned.
+        cudaError_t e2 = cudaFreeAsync(tmp, ctx->stream);
         if(e == cudaSuccess) e = e2;
     }
     if(e != cudaSuccess) {
@@ -457,8 +467,12 @@ int mjx_dropon_from_coefficients(mjx_ctx *ctx, mjx_dropon **out, const mjx_layou
 void mjx_dropon_free(mjx_dropon *d) {
     if(!d) return;
     cudaSetDevice(d->device);
-    if(d->slab) cudaFree(d->slab);
-    if(d->slab2) cudaFree(d->slab2);
+    // stream-ordered free on the calling thread's default stream: the caller guarantees that no launch still
+    // uses the dropon (mj_compose synchronises before it frees; batch hosts free after their own sync), and the
+    // pool only hands the block to another stream once this free has been reached
+    if(d->slab) cudaFreeAsync(d->slab, cudaStreamPerThread);
+    if(d->slab2) cudaFreeAsync(d->slab2, cudaStreamPerThread);
+    cudaGetLastError();
     delete d;
 }
 

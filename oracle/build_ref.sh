@@ -29,11 +29,20 @@ PY
 [ -n "$JPEGSO" ] || { echo "build_ref: no libjpeg .so.62 found in pillow.libs" >&2; exit 1; }
 mkdir -p "$OUT"
 ln -sf "$JPEGSO" "$OUT/libjpeg.so"
+# PNG dropons (WITH_LIBPNG, CMakeLists.txt:18-29): Pillow's libpng16 runtime + third_party/png16/png.h
+PNGSO="$(ls "$(dirname "$JPEGSO")"/libpng16-*.so.16* 2>/dev/null | head -1 || true)"
+PNGFLAGS=""
+PNGLINK=""
+if [ -n "$PNGSO" ]; then
+    ln -sf "$PNGSO" "$OUT/libpng16.so"
+    PNGFLAGS="-DWITH_LIBPNG -I$ROOT/third_party/png16"
+    PNGLINK="-lpng16"
+fi
 gcc -O2 -Wall -Wextra -Wpointer-arith -Wno-uninitialized -Wno-unused-parameter \
-    -Wno-deprecated-declarations -fPIC -shared \
+    -Wno-deprecated-declarations -fPIC -shared $PNGFLAGS \
     -I"$ROOT/third_party/jpeg62" -I"$REF/src" \
     "$REF"/src/compose.c "$REF"/src/convolve.c "$REF"/src/dropon.c \
     "$REF"/src/effect.c "$REF"/src/image.c "$REF"/src/jpeg.c \
     -o "$OUT/libmodjpeg_ref.so" \
-    -L"$OUT" -ljpeg -lm -Wl,-rpath,"$(dirname "$JPEGSO")"
+    -L"$OUT" -ljpeg $PNGLINK -lm -Wl,-rpath,"$(dirname "$JPEGSO")"
 echo "build_ref: built $OUT/libmodjpeg_ref.so against $JPEGSO"

@@ -63,7 +63,8 @@ def test_error_codes_without_touching_the_gpu(built):
     assert j.read_jpeg_from_memory(b"not a jpeg at all") == 5  # MJ_ERR_DECODE_JPEG
     assert j.read_jpeg_from_file("/nonexistent/file.jpg") == 7  # MJ_ERR_FILEIO
     assert d.read_dropon_from_raw(np.zeros((2, 2, 3), np.uint8), 99, 255) == 4  # MJ_ERR_UNSUPPORTED_COLORSPACE
-    assert d.read_dropon_from_memory(b"\x89PNG\r\n\x1a\n0000") == 9  # MJ_ERR_UNSUPPORTED_FILETYPE (no libpng headers here)
+    assert d.read_dropon_from_memory(b"\x89PNG\r\n\x1a\n0000") == 7  # truncated PNG: MJ_ERR_FILEIO (reference: src/dropon.c:170)
+    assert d.read_dropon_from_memory(b"GIF89a0000000000") == 9  # MJ_ERR_UNSUPPORTED_FILETYPE
     assert d.read_dropon_from_memory(b"short") == 2
     rv, out = j.write_jpeg_to_memory(0)
     assert rv == 2
