@@ -160,6 +160,32 @@ class CpuArm:
         return dt
 
 
+def reference_file_pipeline(jpegs, logo, threads: int, images: int) -> float:
+    """decode -> mj_compose -> encode with the unmodified reference, `images` JPEGs over `threads` host threads
+    (one image at a time per thread, as a caller of the reference would); returns wall seconds"""
+    from oracle import oracle_py as O
+
+    lib = O.Reference()
+    drops = [lib.dropon_from_raw(logo, O.CS_RGBA, 255) for _ in range(threads)]
+    errs = []
+
+    def work(t):
+        for i in range(t, images, threads):
+            j = lib.read_jpeg(jpegs[i % len(jpegs)])
+            if j.compose(drops[t], ALIGN_TOP_LEFT, 0, 0) != 0:
+                errs.append(i)
+            j.write(0)
+
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    dt = time.perf_counter() - t0
+    if errs:
+        raise RuntimeError(f"reference pipeline failed on images {errs[:3]}")
+    return dt
+
+
 def host_threads() -> int:
     try:
         n = len(os.sched_getaffinity(0))
@@ -450,6 +476,34 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
     roi_bytes = sum(cd.dims(c)[0] * cd.dims(c)[1] * 128 for c in range(3))
     engine.host_free(pinned)
 
+    # ---- tier (iii): JPEG bytes in -> JPEG bytes out through mj_compose_batch (rank 0, N = 1 only) ------
+    files = None
+    if rank == 0 and world == 1 and args.file_images > 0:
+        if ORIG_AFFINITY:
+            os.sched_setaffinity(0, ORIG_AFFINITY)  # entropy coding uses every host core, for both arms
+        threads = host_threads()
+        d = M.Dropon()
+        assert d.read_dropon_from_raw(logo, M.CS_RGBA, 255) == 0
+        batch = [jpegs[i % len(jpegs)] for i in range(args.file_images)]
+        capi.compose_batch(batch[:4 * threads], d, ALIGN_TOP_LEFT, 0, 0, 0, nthreads=threads)  # warm the page-locked slab (one full window)
+        tm = {}
+        rvb, status, outs = capi.compose_batch(batch, d, ALIGN_TOP_LEFT, 0, 0, 0, nthreads=threads, timing=tm)
+        tf = tm["call_s"]  # wall time of the C call (JPEG bytes in -> malloc()ed JPEG bytes out)
+        assert rvb == 0 and not any(status), (rvb, status[:8])
+        files = {"images": args.file_images, "threads": threads, "images_per_s": args.file_images / tf,
+                 "mblocks_per_s": args.file_images * blocks_per_image / tf / 1e6,
+                 "path": "mj_compose_batch: libjpeg entropy decode (thread pool) -> K1 once -> K2 one launch per window, zero-copy "
+                         "on a page-locked slab -> libjpeg entropy encode (thread pool); JPEG bytes in, JPEG bytes out",
+                 "bytes_in": sum(len(b) for b in batch), "bytes_out": sum(len(o) for o in outs)}
+        if not args.no_cpu_baseline:
+            try:
+                nref = max(threads, min(args.file_images, 2 * threads))
+                dtr = reference_file_pipeline(jpegs, logo, threads, nref)
+                files["reference"] = {"images": nref, "threads": threads, "images_per_s": nref / dtr,
+                                      "path": "unmodified reference: mj_read_jpeg_from_memory -> mj_compose -> mj_write_jpeg_to_memory per image"}
+            except Exception as e:
+                files["reference"] = {"unavailable": str(e)[:200]}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -516,6 +570,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
                                   "what": "whole K2 step = k2_simple_kernel + k2_generic_kernel back to back"},
                          "kernels": kernels},
             "other_kernels": other,
+            "e2e_files": files,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_mbps, "unit": "Mblocks/s",
                     # zero-copy: only touched blocks cross PCIe (G read + written, OPAQUE/U written; U also read)
@@ -548,6 +603,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-kernels", action="store_true")
+    ap.add_argument("--file-images", type=int, default=256, help="JPEGs pushed through mj_compose_batch (tier iii); 0 = skip")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -137,6 +137,20 @@ int mj_effect_pixelate(mj_jpeg_t *m);
 int mj_effect_tint(mj_jpeg_t *m, int cb_value, int cr_value);
 int mj_effect_luminance(mj_jpeg_t *m, int value);
 
+/* ---- additive: batch pipeline (not in the reference) ------------------------------------
+ * n JPEGs in memory, one dropon, one placement: entropy decode and encode on a pool of `nthreads` host threads,
+ * the dropon compiled once per image geometry (K1) and blended by ONE K2 launch per window of images.  Per image
+ * this is mj_read_jpeg_from_memory + mj_compose + mj_write_jpeg_to_memory (same results); out[i].data is
+ * malloc()ed for the caller, status[i] is that image's MJ_* code.  The return value reports batch-level failures
+ * only (arguments, memory, no device). */
+typedef struct {
+    unsigned char *data;
+    size_t         len;
+} mj_blob_t;
+
+int mj_compose_batch(int n, const mj_blob_t *in, mj_blob_t *out, int *status, mj_dropon_t *d, unsigned int align, int offset_x,
+                     int offset_y, int write_options, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

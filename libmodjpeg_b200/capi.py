@@ -422,6 +422,7 @@ def load_modjpeg() -> C.CDLL:
     L.mjx_jpeg_export_plane.argtypes = [vp, C.c_int, vp]
     L.mjx_jpeg_import_plane.argtypes = [vp, C.c_int, vp]
     L.mjx_jpeg_layout.argtypes = [vp, C.POINTER(Layout)]
+    L.mj_compose_batch.argtypes = [C.c_int, C.POINTER(Blob), C.POINTER(Blob), C.POINTER(C.c_int), vp, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int]
     L.mjx_host_ctx.argtypes = []
     L.mjx_host_ctx.restype = vp
     _lib_mj = L
@@ -531,6 +532,36 @@ class Jpeg:
             self.free()
         except Exception:
             pass
+
+
+class Blob(C.Structure):
+    """mj_blob_t (include/libmodjpeg.h)"""
+    _fields_ = [("data", C.c_void_p), ("len", C.c_size_t)]
+
+
+def compose_batch(jpegs: list[bytes], dropon: "Dropon", align: int, offset_x: int = 0, offset_y: int = 0, options: int = 0,
+                  nthreads: int = 1, timing: dict | None = None) -> tuple[int, list[int], list[bytes | None]]:
+    """mj_compose_batch: decode -> compose -> encode for many JPEGs and one dropon.  Returns (rv, status[], outputs[]);
+    timing["call_s"] receives the wall time of the C call alone (without this wrapper's copies into Python bytes)."""
+    import time
+
+    L = load_modjpeg()
+    n = len(jpegs)
+    cin = (Blob * max(n, 1))(*[Blob(C.cast(C.c_char_p(j), C.c_void_p).value, len(j)) for j in jpegs])  # no copy: points into the bytes
+    cout = (Blob * max(n, 1))()
+    status = (C.c_int * max(n, 1))()
+    t0 = time.perf_counter()
+    rv = L.mj_compose_batch(n, cin, cout, status, dropon.ptr, align, offset_x, offset_y, options, nthreads)
+    if timing is not None:
+        timing["call_s"] = time.perf_counter() - t0
+    outs: list[bytes | None] = []
+    for i in range(n):
+        if cout[i].data:
+            outs.append(C.string_at(cout[i].data, cout[i].len))
+            _libc.free(cout[i].data)
+        else:
+            outs.append(None)
+    return rv, list(status[:n]), outs
 
 
 class Dropon:

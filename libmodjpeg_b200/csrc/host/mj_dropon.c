@@ -128,7 +128,8 @@ static int dropon_from_png(mj_dropon_t *d, const unsigned char *memory, size_t l
         return MJ_ERR_DROPON_DIMENSIONS;
     }
     image.format = PNG_FORMAT_RGBA;
-    unsigned char *rgba = (unsigned char *)malloc(PNG_IMAGE_SIZE(image) ? PNG_IMAGE_SIZE(image) : 1);
+    const size_t   nbytes = PNG_IMAGE_SIZE(image);
+    unsigned char *rgba = (unsigned char *)malloc(nbytes > 0 ? nbytes : 1);
     if(rgba == NULL) {
         png_image_free(&image);
         return MJ_ERR_MEMORY;

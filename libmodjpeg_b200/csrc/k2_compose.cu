@@ -468,8 +468,7 @@ __global__ void __launch_bounds__(kGWarps * 32, kMinCtas) k2_generic_kernel(cons
                 const unsigned char      *src = sb + (lane >> 3) * kInStride + (lane & 7) * 16;
                 const unsigned long long *ap = addr + (lane >> 3);
                 const unsigned            coff = (lane & 7) * 16;
-#pragma unroll
-                unsigned long long b[8];
+                unsigned long long        b[8];
                 uint4              v[8];
 #pragma unroll
                 for(int j = 0; j < 8; j++) {

@@ -112,6 +112,7 @@ void mjx_ctx_destroy(mjx_ctx *ctx) {
         }
     }
     if(ctx->pin) cudaFreeHost(ctx->pin);
+    if(ctx->pin2) cudaFreeHost(ctx->pin2);
     if(ctx->dev) cudaFree(ctx->dev);
     if(ctx->desc_dev) cudaFree(ctx->desc_dev);
     if(ctx->scratch) cudaFree(ctx->scratch);
@@ -166,6 +167,15 @@ int mjx_host_alloc(mjx_ctx *ctx, void **ptr, size_t bytes) {
 
 void mjx_host_free(mjx_ctx *ctx, void *ptr) {
     if(ctx && ptr && use_device(ctx) == MJX_OK) cudaFreeHost(ptr);
+}
+
+int mjx_ctx_pinned_scratch(mjx_ctx *ctx, size_t bytes, void **ptr) {
+    int rv = use_device(ctx);
+    if(rv) return rv;
+    if(!ptr) return MJX_ERR_ARG;
+    if((rv = grow(ctx, &ctx->pin2, &ctx->pin2_bytes, bytes ? bytes : 1, true)) != MJX_OK) return rv;
+    *ptr = ctx->pin2;
+    return MJX_OK;
 }
 
 int mjx_copy_h2d(mjx_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {

@@ -79,6 +79,8 @@ struct mjx_ctx {
     // staging pools for the host-pointer entry points (grown on demand, reused across calls)
     void  *pin = nullptr;
     size_t pin_bytes = 0;
+    void  *pin2 = nullptr; // caller-visible page-locked scratch (mjx_ctx_pinned_scratch)
+    size_t pin2_bytes = 0;
     void  *dev = nullptr;
     size_t dev_bytes = 0;
     void  *desc_dev = nullptr; // device array of mjx_image_desc_t for staged launches

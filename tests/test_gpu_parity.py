@@ -554,3 +554,44 @@ def test_k2_fast_equals_strict_on_encoder_produced_jpegs(engine):
         cls_maps = [cd.download(c)[2] for c in range(3)]
         _check_planes(fast, strict, planes, cls_maps, (g["block_x"], g["block_y"]), samp, ("fast-vs-strict", subs))
         cd.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# the batch pipeline: mj_compose_batch == read + mj_compose + write, image by image
+# ---------------------------------------------------------------------------------------------
+
+
+def test_compose_batch_pipeline_equals_per_image_api(engine):
+    import libmodjpeg_b200 as M
+    from libmodjpeg_b200 import capi
+
+    raw = util.logo_rgba(200, 120, tile=64, radius=27)
+    d = M.Dropon()
+    assert d.read_dropon_from_raw(raw, M.CS_RGBA, 255) == 0
+    # two geometries and one undecodable input in one batch
+    jpegs = [util.jpeg_bytes(320, 240, "420", 85, seed=300 + i) for i in range(5)] + \
+            [util.jpeg_bytes(272, 208, "444", 90, seed=310 + i) for i in range(3)] + [b"definitely not a jpeg"]
+    order = [0, 5, 1, 8, 6, 2, 3, 7, 4]
+    batch = [jpegs[i] for i in order]
+    rv, status, outs = capi.compose_batch(batch, d, M.ALIGN_CENTER, 7, -5, 0, nthreads=4)
+    assert rv == 0
+    for k, i in enumerate(order):
+        if i == 8:
+            assert status[k] == 5 and outs[k] is None  # MJ_ERR_DECODE_JPEG, the rest of the batch is unaffected
+            continue
+        assert status[k] == 0
+        j = M.Jpeg()
+        assert j.read_jpeg_from_memory(jpegs[i]) == 0
+        assert j.compose(d, M.ALIGN_CENTER, 7, -5) == 0
+        rvw, want = j.write_jpeg_to_memory(0)
+        assert rvw == 0
+        assert outs[k] == want, (k, i)  # same kernels, same libjpeg: byte-identical files
+    # blend == 0: the pipeline is a pure transcode
+    d0 = M.Dropon()
+    assert d0.read_dropon_from_raw(raw[:, :, :3].copy(), M.CS_RGB, 0) == 0
+    rv, status, outs = capi.compose_batch(jpegs[:2], d0, M.ALIGN_CENTER, 0, 0, 0, nthreads=2)
+    assert rv == 0 and status == [0, 0]
+    for o, src in zip(outs, jpegs[:2]):
+        j = M.Jpeg()
+        assert j.read_jpeg_from_memory(src) == 0
+        assert j.write_jpeg_to_memory(0)[1] == o
