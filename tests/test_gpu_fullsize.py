@@ -156,6 +156,36 @@ def test_c4_fullframe_generic_vs_oracle(engine, port, gray):
     assert bad <= n * 2e-4
 
 
+@pytest.mark.parametrize("blend", [128, 255])
+def test_c4_fullframe_uniform_alpha_8k_bitexact(engine, port, blend):
+    """config 4 (i): 7680x4320 4:4:4, full-frame overlay with one alpha for every pixel -- 1 555 200 blocks of class
+    U (blend 128) or OPAQUE (blend 255) through the streaming kernel, bit-exact against the oracle at the full size"""
+    import libmodjpeg_b200 as M
+
+    W_, H_ = 7680, 4320
+    data = util.jpeg_bytes(W_, H_, "444", 85, seed=5)
+    rng = np.random.default_rng(6)
+    small = rng.integers(0, 256, size=(H_ // 8, W_ // 8, 3), dtype=np.uint8)
+    raw = np.ascontiguousarray(np.repeat(np.repeat(small, 8, 0), 8, 1))  # blocky RGB overlay, no alpha channel
+    j = M.Jpeg()
+    assert j.read_jpeg_from_memory(data) == 0
+    info, samp = j.info(), j.sampling()
+    want = j.planes()
+    q = [j.qtable(c) for c in range(3)]
+    i3, a3, cs, sblend = util.ingest_raw(raw, 1, blend)
+    rv, g, D, W = util.oracle_compose(port, want, q, W_, H_, info["colorspace"], samp, i3, a3, cs, sblend, 4 | 1, 0, 0)
+    assert rv == 0
+    d = M.Dropon()
+    assert d.read_dropon_from_raw(raw, M.CS_RGB, blend) == 0
+    before = j.planes()
+    assert j.compose(d, 4 | 1, 0, 0) == 0
+    changed = 0
+    for c, got in enumerate(j.planes()):
+        assert np.array_equal(got, want[c]), (blend, c)
+        changed += int((got != before[c]).sum())
+    assert changed > 1_000_000
+
+
 def test_c5_effects_24mp_vs_oracle(engine, port):
     """config 5: the four effects on a 24 MP 4:2:0 JPEG through the API, bit-exact"""
     import libmodjpeg_b200 as M
