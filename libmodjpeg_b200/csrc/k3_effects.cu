@@ -44,38 +44,51 @@ __device__ __forceinline__ int fold_dc(const K3Params &p, int dc, int q0) {
 
 static constexpr int kThreads = 256;
 
-// component ends with AC == 0: 8 lanes per block, every lane stores its (zero) row
+// component ends with AC == 0: 8 lanes per block, every lane stores its (zero) row; a CTA owns whole block rows
 __global__ void __launch_bounds__(kThreads) k3_rewrite_kernel(const K3Params p, int first_is_zero) {
     const mjx_image_desc_t &im = p.items[blockIdx.y];
     const int c = p.comp, r = threadIdx.x & 7;
-    const int wreal = im.wreal[c], nblk = wreal * im.hreal[c], stride = im.stride_blocks[c];
+    const int wreal = im.wreal[c], hreal = im.hreal[c], stride = im.stride_blocks[c];
     const int q0 = im.q[c][0];
     int16_t  *plane = reinterpret_cast<int16_t *>(im.plane[c]);
-    for(int bi = blockIdx.x * (kThreads / 8) + (threadIdx.x >> 3); bi < nblk; bi += gridDim.x * (kThreads / 8)) {
-        const int l = bi / wreal, k = bi - l * wreal;
-        int16_t  *bp = plane + ((size_t)l * stride + k) * 64;
-        Row8      row;
-        row.w[0] = row.w[1] = row.w[2] = row.w[3] = 0;
-        if(r == 0) {
-            int dc = first_is_zero ? 0 : (int)bp[0];
-            dc = fold_dc(p, dc, q0);
-            row.w[0] = (uint32_t)dc & 0xffffu;
+    for(int l = blockIdx.x; l < hreal; l += gridDim.x) {
+        int16_t *rowp = plane + (size_t)l * stride * 64;
+        for(int k = threadIdx.x >> 3; k < wreal; k += kThreads / 8) {
+            int16_t *bp = rowp + (size_t)k * 64;
+            Row8     row;
+            row.w[0] = row.w[1] = row.w[2] = row.w[3] = 0;
+            if(r == 0) {
+                int dc = first_is_zero ? 0 : (int)bp[0];
+                dc = fold_dc(p, dc, q0);
+                row.w[0] = (uint32_t)dc & 0xffffu;
+            }
+            st_row_stream(bp + r * 8, row);
         }
-        st_row_stream(bp + r * 8, row);
     }
 }
 
-// DC-only pipeline: one thread per block
+// DC-only pipeline: one thread per block.  A CTA owns block rows l = blockIdx.x, blockIdx.x + gridDim.x, ..;
+// its threads walk the columns, four rows at a time so that four independent 2-byte loads are in flight per
+// thread (the pass moves one 32-byte DRAM sector each way per 128-byte block: it lives on memory parallelism).
 __global__ void __launch_bounds__(kThreads) k3_dc_kernel(const K3Params p) {
     const mjx_image_desc_t &im = p.items[blockIdx.y];
     const int c = p.comp;
-    const int wreal = im.wreal[c], nblk = wreal * im.hreal[c], stride = im.stride_blocks[c];
+    const int wreal = im.wreal[c], hreal = im.hreal[c], stride = im.stride_blocks[c];
     const int q0 = im.q[c][0];
     int16_t  *plane = reinterpret_cast<int16_t *>(im.plane[c]);
-    for(int bi = blockIdx.x * kThreads + threadIdx.x; bi < nblk; bi += gridDim.x * kThreads) {
-        const int l = bi / wreal, k = bi - l * wreal;
-        int16_t  *bp = plane + ((size_t)l * stride + k) * 64;
-        bp[0] = (int16_t)fold_dc(p, (int)bp[0], q0);
+    for(int l0 = blockIdx.x * 4; l0 < hreal; l0 += gridDim.x * 4) {
+        for(int k = threadIdx.x; k < wreal; k += kThreads) {
+            int16_t *bp[4];
+            int      dc[4];
+#pragma unroll
+            for(int u = 0; u < 4; u++) {
+                bp[u] = plane + ((size_t)(l0 + u) * stride + k) * 64;
+                dc[u] = (l0 + u < hreal) ? (int)*bp[u] : 0;
+            }
+#pragma unroll
+            for(int u = 0; u < 4; u++)
+                if(l0 + u < hreal) *bp[u] = (int16_t)fold_dc(p, dc[u], q0);
+        }
     }
 }
 
@@ -96,10 +109,10 @@ cudaError_t launch_k3(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, 
             if(ops[i].op == MJX_FX_ZERO || ops[i].op == MJX_FX_PIXELATE) rewrite = true;
         }
         if(p.nops == 0) continue;
-        // enough CTAs per image to fill 148 SMs a few times over; each CTA strides over its image
-        int gx = (148 * 16 + n - 1) / n;
+        // CTAs per image: enough for 148 SMs x 8 resident CTAs a few times over; each CTA strides over block rows
+        int gx = (148 * 32 + n - 1) / n;
         if(gx < 1) gx = 1;
-        if(gx > 4096) gx = 4096;
+        if(gx > 1024) gx = 1024;
         for(int first = 0; first < n; first += 65535) {
             const int cnt = n - first < 65535 ? n - first : 65535;
             p.items = items_dev + first;
