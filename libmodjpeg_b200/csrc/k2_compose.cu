@@ -33,8 +33,6 @@
 //
 // Roofline: HBM.  Algorithmic bytes per block: T 0, OPAQUE 128 (write), U/G 256 (read + write),
 // plus the compiled dropon once per launch (L2 / shared-memory resident across the images).
-#include <stdlib.h>
-
 #include "mjx_device.cuh"
 
 namespace mjx {
@@ -512,16 +510,14 @@ cudaError_t launch_k2(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, 
     }
     if(view.n_simple == 0 && view.n_generic == 0) return cudaSuccess;
 
-    // CTA shape of the generic kernel: 4 warps x 3 CTAs/SM (default) or 8 warps x 2 CTAs/SM (MJX_K2_WARPS=8, an experiment knob)
-    static int  ctas_per_sm = 0, g_warps = 4; // idempotent; a benign race at worst computes them twice
-    static void (*g_kernel)(const FastParams) = nullptr;
+    // generic kernel: 4 warps per CTA, 3 CTAs per SM (142 registers, 60 KB shared memory).  8 warps x 2 CTAs at 128
+    // registers was measured slower (1.89 vs 1.72 ms): the spills cost more than the extra warps hide.
+    constexpr int g_warps = 4;
+    static int    ctas_per_sm = 0; // idempotent; a benign race at worst computes it twice
     if(ctas_per_sm == 0) {
-        const char *env = getenv("MJX_K2_WARPS");
-        g_warps = (env && atoi(env) == 8) ? 8 : 4;
-        g_kernel = g_warps == 8 ? k2_generic_kernel<8, 2> : k2_generic_kernel<4, 3>;
-        if((e = cudaFuncSetAttribute(g_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem(g_warps))) != cudaSuccess) return e;
+        if((e = cudaFuncSetAttribute(k2_generic_kernel<g_warps, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem(g_warps))) != cudaSuccess) return e;
         int occ = 0;
-        if((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, g_kernel, g_warps * 32, g_smem(g_warps))) != cudaSuccess) return e;
+        if((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_generic_kernel<g_warps, 3>, g_warps * 32, g_smem(g_warps))) != cudaSuccess) return e;
         ctas_per_sm = occ > 0 ? occ : 1;
     }
     FastParams p;
@@ -531,7 +527,7 @@ cudaError_t launch_k2(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, 
     p.n = n;
     p.block_x = block_x;
     p.block_y = block_y;
-    p.images_per_item = n < 16 * g_warps ? n : 16 * g_warps; // <= 32 per warp (one descriptor per lane)
+    p.images_per_item = n < 24 * g_warps ? n : 24 * g_warps; // per warp: <= 32 (one descriptor per lane); 16..32 measured within 1.5 %
 
     if(view.n_simple > 0 && (class_mask & 1)) {
         const unsigned tiles = (unsigned)(view.n_simple / 32);
@@ -551,7 +547,7 @@ cudaError_t launch_k2(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, 
         if(nitems > 0x7fffffffLL) return cudaErrorInvalidValue;
         const int sms = sm_count > 0 ? sm_count : 148;
         const int ctas = nitems < (long long)sms * ctas_per_sm ? (int)nitems : sms * ctas_per_sm;
-        g_kernel<<<ctas, g_warps * 32, g_smem(g_warps), s>>>(p);
+        k2_generic_kernel<g_warps, 3><<<ctas, g_warps * 32, g_smem(g_warps), s>>>(p);
         if((e = cudaGetLastError()) != cudaSuccess) return e;
         if(launches) (*launches)++;
     }
