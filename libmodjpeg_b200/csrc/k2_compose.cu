@@ -10,18 +10,20 @@
 //           the closed form of the reference's 64 sparse DCT-domain products, within +-1
 //           quantisation step of it.
 //
-// Three kernels per call (one launch each, any number of images):
-//   k2_tables_kernel   per (image, component): q as float, q * IDCT prescale, biased 1/q
+// Two kernels per call (one launch each, any number of images):
 //   k2_simple_kernel   OPAQUE/U list; 8 lanes per block (lane r = row r, one 128-bit access per
-//                      plane), D row kept in registers while the lanes walk the images
-//   k2_generic_kernel  G list; one thread owns one block (all 64 coefficients in registers, so
-//                      the 2-D transforms need no shuffles), one warp owns a tile of 32 list
-//                      entries whose A and Ds stay in shared memory while the warp streams the
-//                      images through: cp.async double buffering of the 32 image blocks (4 KB) of
-//                      the next image, XOR-swizzled so that the thread-per-block 128-bit shared
-//                      loads are bank-conflict free; results go back through the same buffer so
-//                      global stores are coalesced.  Work (tile x image chunk) is claimed from an
-//                      atomic counter by persistent warps, one 6-warp CTA per SM.
+//                      plane), D row kept in registers while the lanes walk 16 images whose quant
+//                      tables were converted once per CTA into shared memory; built for memory
+//                      parallelism (3.6 TB/s write-only)
+//   k2_generic_kernel  G list; one thread owns one block (all 64 coefficients in registers as 32
+//                      fp32 pairs, so the 2-D transforms need no shuffles), arithmetic on packed
+//                      fp32 (FADD2 / FMUL2 / FFMA2).  A CTA of 4 warps shares a tile of 32 list
+//                      entries (A and Ds in shared memory) and streams the images through a
+//                      cp.async double buffer per warp; shared-memory blocks are padded so the
+//                      thread-per-block 128-bit accesses are conflict-free at immediate offsets;
+//                      results go back through the same buffer so global stores are coalesced.
+//                      Work (tile x image chunk) is claimed from an atomic counter by persistent
+//                      CTAs, 3 per SM.  Details at the kernel.
 //   The arithmetic stays in the fp32 pipe: on sm_100a F2I/FRND issue at 1/8 rate and I2F.S16/SHFL
 //   at 1/4 (profiles/microbench/ubench.txt), so truncation and int16 packing use magic-number adds.
 //
