@@ -15,8 +15,8 @@
  * and the library must be compiled against the same <jpeglib.h> (here: the ABI-62 header in
  * third_party/jpeg62, matching the libjpeg-turbo 3.1.x runtime in this image).
  */
-#ifndef _LIBMODJPEG_H_
-#define _LIBMODJPEG_H_
+#ifndef MODJPEG_B200_LIBMODJPEG_H
+#define MODJPEG_B200_LIBMODJPEG_H
 
 /* stdio.h must precede jpeglib.h (size_t, FILE) */
 #include <stdio.h>
@@ -26,51 +26,57 @@
 extern "C" {
 #endif
 
-/* reference: src/libmodjpeg.h:33-36 (the reference header still says 1.0.0) */
-#define MJ_LIB_VERSION_MAJOR   1
-#define MJ_LIB_VERSION_MINOR   0
+/* API level implemented: the reference's header says 1.0.0 (reference: src/libmodjpeg.h:33-36) */
+#define MJ_LIB_VERSION_MAJOR 1
+#define MJ_LIB_VERSION_MINOR 0
 #define MJ_LIB_VERSION_RELEASE 0
-#define MJ_LIB_VERSION         10000
+#define MJ_LIB_VERSION (MJ_LIB_VERSION_MAJOR * 10000 + MJ_LIB_VERSION_MINOR * 100 + MJ_LIB_VERSION_RELEASE)
 
-/* raw dropon pixel formats accepted by mj_read_dropon_from_raw (reference: :38-43) */
-#define MJ_COLORSPACE_RGB        1
-#define MJ_COLORSPACE_RGBA       2
-#define MJ_COLORSPACE_GRAYSCALE  3
-#define MJ_COLORSPACE_GRAYSCALEA 4
-#define MJ_COLORSPACE_YCC        5
-#define MJ_COLORSPACE_YCCA       6
+/* The numeric values below are the reference's ABI (reference: src/libmodjpeg.h:38-69). */
 
-/* placement bits for mj_compose (reference: :45-49) */
-#define MJ_ALIGN_LEFT   (1 << 0)
-#define MJ_ALIGN_RIGHT  (1 << 1)
-#define MJ_ALIGN_TOP    (1 << 2)
-#define MJ_ALIGN_BOTTOM (1 << 3)
-#define MJ_ALIGN_CENTER (1 << 4)
+enum { /* pixel formats of mj_read_dropon_from_raw: odd = no alpha byte, even = trailing alpha byte */
+    MJ_COLORSPACE_RGB = 1,
+    MJ_COLORSPACE_RGBA,
+    MJ_COLORSPACE_GRAYSCALE,
+    MJ_COLORSPACE_GRAYSCALEA,
+    MJ_COLORSPACE_YCC,
+    MJ_COLORSPACE_YCCA
+};
 
-/* blend values (reference: :51-53) */
-#define MJ_BLEND_NONUNIFORM -1
-#define MJ_BLEND_NONE       0
-#define MJ_BLEND_FULL       255
+enum { /* placement bits of mj_compose; neither LEFT nor RIGHT (TOP nor BOTTOM) set means centred on that axis */
+    MJ_ALIGN_LEFT = 0x01,
+    MJ_ALIGN_RIGHT = 0x02,
+    MJ_ALIGN_TOP = 0x04,
+    MJ_ALIGN_BOTTOM = 0x08,
+    MJ_ALIGN_CENTER = 0x10
+};
 
-/* mj_write_jpeg_* options (reference: :55-58; the misspelling is the reference's) */
-#define MJ_OPTION_NONE        0
-#define MJ_OPTION_OPTIMIZE    (1 << 0)
-#define MJ_OPTION_PROGRESSIVE (1 << 1)
-#define MJ_OPTION_ARITHMETRIC (1 << 2)
+enum { /* mj_dropon_t.blend */
+    MJ_BLEND_NONUNIFORM = -1, /* per-pixel alpha */
+    MJ_BLEND_NONE = 0,        /* fully transparent: mj_compose is a no-op */
+    MJ_BLEND_FULL = 255       /* fully opaque */
+};
 
-/* return codes (reference: :60-69) */
-#define MJ_OK                         0
-#define MJ_ERR_MEMORY                 1
-#define MJ_ERR_NULL_DATA              2
-#define MJ_ERR_DROPON_DIMENSIONS      3
-#define MJ_ERR_UNSUPPORTED_COLORSPACE 4
-#define MJ_ERR_DECODE_JPEG            5
-#define MJ_ERR_ENCODE_JPEG            6
-#define MJ_ERR_FILEIO                 7
-#define MJ_ERR_IMAGE_SIZE             8
-#define MJ_ERR_UNSUPPORTED_FILETYPE   9
-/* additive: the CUDA device / extension is missing or a kernel launch failed */
-#define MJ_ERR_DEVICE                 10
+enum { /* flags of mj_write_jpeg_* (ARITHMETRIC is the reference's spelling) */
+    MJ_OPTION_NONE = 0,
+    MJ_OPTION_OPTIMIZE = 0x1,
+    MJ_OPTION_PROGRESSIVE = 0x2,
+    MJ_OPTION_ARITHMETRIC = 0x4
+};
+
+enum { /* return codes */
+    MJ_OK = 0,
+    MJ_ERR_MEMORY,
+    MJ_ERR_NULL_DATA,
+    MJ_ERR_DROPON_DIMENSIONS,
+    MJ_ERR_UNSUPPORTED_COLORSPACE,
+    MJ_ERR_DECODE_JPEG,
+    MJ_ERR_ENCODE_JPEG,
+    MJ_ERR_FILEIO,
+    MJ_ERR_IMAGE_SIZE,
+    MJ_ERR_UNSUPPORTED_FILETYPE,
+    MJ_ERR_DEVICE /* 10, additive: no usable CUDA device, or a kernel launch failed */
+};
 
 /* sampling description of a decoded JPEG (reference: :71-84) */
 typedef struct {
@@ -111,31 +117,46 @@ typedef struct {
     int blend; /* 0..255 uniform, or MJ_BLEND_NONUNIFORM when the pixels carry alpha */
 } mj_dropon_t;
 
-/* dropon ingest -- host side (reference: src/dropon.c:33-323,578-604) */
-void mj_init_dropon(mj_dropon_t *d);
-int  mj_read_dropon_from_raw(mj_dropon_t *d, const unsigned char *rawdata, unsigned int colorspace, int width, int height, short blend);
-int  mj_read_dropon_from_memory(mj_dropon_t *d, const unsigned char *memory, size_t len, const unsigned char *maskmemory, size_t masklen, short blend);
-int  mj_read_dropon_from_file(mj_dropon_t *d, const char *filename, const char *maskfilename, short blend);
+/* ---- overlay ingest: host side, one-time (reference: src/dropon.c:33-323,578-604) ---------------------------
+ * mj_init_dropon() zeroes a caller-allocated struct (required before first use); the readers release whatever
+ * the struct held, then fill it.  `pixels` of the raw reader is copied. */
+void mj_init_dropon(mj_dropon_t *dropon);
+void mj_free_dropon(mj_dropon_t *dropon);
+int  mj_read_dropon_from_raw(mj_dropon_t         *dropon,
+                             const unsigned char *pixels,      /* width * height * (1 | 2 | 3 | 4) bytes */
+                             unsigned int         pixel_format, /* MJ_COLORSPACE_* */
+                             int                  width,
+                             int                  height,
+                             short                blend);
+int  mj_read_dropon_from_memory(mj_dropon_t         *dropon,
+                                const unsigned char *file_bytes, /* a JPEG or PNG file image */
+                                size_t               nbytes,
+                                const unsigned char *mask_bytes, /* optional grayscale JPEG used as alpha (JPEG dropons) */
+                                size_t               mask_nbytes,
+                                short                blend);
+int  mj_read_dropon_from_file(mj_dropon_t *dropon, const char *path, const char *mask_path, short blend);
 
-/* JPEG coefficient I/O -- host libjpeg (reference: src/image.c:33-255) */
-void mj_init_jpeg(mj_jpeg_t *m);
-int  mj_read_jpeg_from_memory(mj_jpeg_t *m, const unsigned char *memory, size_t len, size_t max_pixel);
-int  mj_read_jpeg_from_file(mj_jpeg_t *m, const char *filename, size_t max_pixel);
+/* ---- JPEG coefficient I/O: host libjpeg entropy decode / encode (reference: src/image.c:33-255) ------------
+ * max_pixel: refuse images with more pixels (0 = no limit).  mj_write_jpeg_to_memory() hands a malloc()ed
+ * buffer to the caller. */
+void mj_init_jpeg(mj_jpeg_t *jpeg);
+void mj_free_jpeg(mj_jpeg_t *jpeg);
+int  mj_read_jpeg_from_memory(mj_jpeg_t *jpeg, const unsigned char *file_bytes, size_t nbytes, size_t max_pixel);
+int  mj_read_jpeg_from_file(mj_jpeg_t *jpeg, const char *path, size_t max_pixel);
+int  mj_write_jpeg_to_memory(mj_jpeg_t *jpeg, unsigned char **out_bytes, size_t *out_nbytes, int options);
+int  mj_write_jpeg_to_file(mj_jpeg_t *jpeg, char *path, int options);
 
-/* DCT-domain compositing -- B200 kernels K1 + K2 (reference: src/compose.c:33-180) */
-int mj_compose(mj_jpeg_t *m, mj_dropon_t *d, unsigned int align, int offset_x, int offset_y);
+/* ---- DCT-domain compositing: kernels K1 + K2 on the GPU (reference: src/compose.c:33-180) ------------------
+ * Blends `dropon` into the coefficients of `jpeg` at the place given by the MJ_ALIGN_* bits plus a pixel
+ * offset; returns when jpeg->coef holds the result. */
+int mj_compose(mj_jpeg_t *jpeg, mj_dropon_t *dropon, unsigned int align, int offset_x, int offset_y);
 
-int mj_write_jpeg_to_memory(mj_jpeg_t *m, unsigned char **memory, size_t *len, int options);
-int mj_write_jpeg_to_file(mj_jpeg_t *m, char *filename, int options);
-
-void mj_free_jpeg(mj_jpeg_t *m);
-void mj_free_dropon(mj_dropon_t *d);
-
-/* coefficient effects -- B200 kernel K3 (reference: src/effect.c:28-222) */
-int mj_effect_grayscale(mj_jpeg_t *m);
-int mj_effect_pixelate(mj_jpeg_t *m);
-int mj_effect_tint(mj_jpeg_t *m, int cb_value, int cr_value);
-int mj_effect_luminance(mj_jpeg_t *m, int value);
+/* ---- coefficient effects: kernel K3 on the GPU (reference: src/effect.c:28-222) ----------------------------
+ * grayscale / tint / luminance act on YCbCr images only (MJ_OK and no change otherwise). */
+int mj_effect_grayscale(mj_jpeg_t *jpeg);                 /* drop all chroma */
+int mj_effect_pixelate(mj_jpeg_t *jpeg);                  /* keep only the DC of every block */
+int mj_effect_tint(mj_jpeg_t *jpeg, int cb_add, int cr_add); /* add to the chroma DCs */
+int mj_effect_luminance(mj_jpeg_t *jpeg, int y_add);      /* add to the luma DC */
 
 /* ---- additive: batch pipeline (not in the reference) ------------------------------------
  * n JPEGs in memory, one dropon, one placement: entropy decode and encode on a pool of `nthreads` host threads,
