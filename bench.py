@@ -46,6 +46,25 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE line, the JSON result: file descriptor 1 is pointed at stderr for the whole run (NCCL prints
+# its version banner with printf, libjpeg and the reference print warnings) and the result goes to the saved descriptor.
+_RESULT_OUT = None
+
+
+def capture_stdout() -> None:
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 # ------------------------------------------------------------------------------------------
 # synthetic inputs: 16 distinct 1080p 4:2:0 q85 bases cycled over the batch
 # ------------------------------------------------------------------------------------------
@@ -72,7 +91,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -220,7 +239,7 @@ def run_reference_arm(args, rank: int, world: int):
         "e2e": {"value": mbps, "unit": "Mblocks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -357,7 +376,6 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
     launches = engine.kernel_launches - launches0
     total_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
     tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -380,6 +398,9 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
 
     ms_simple = time_masked(1) if counts["OPAQUE"] + counts["U"] else 0.0
     ms_generic = time_masked(2) if counts["G"] else 0.0
+    # clocks / throttle reasons sampled from just before the timed steps to the end of the per-kernel timings
+    # (the same kernels back to back: the GPU is under the bench's load for the whole window)
+    clocks = sampler.stop(t0, time.time()) if rank == 0 else None
 
     # ---- the other two kernels of the path, on the same resident batch (rank 0 reports) -----------
     other = {}
@@ -586,7 +607,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
             "gpu_launches": launches,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -608,6 +629,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    capture_stdout()
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
