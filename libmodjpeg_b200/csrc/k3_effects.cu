@@ -24,6 +24,7 @@ struct K3Params {
     int                     nops;   // steps that apply to `comp`, in order
     int                     op[kMaxOps];
     int                     value[kMaxOps];
+    const int16_t          *dc_compact; // rewrite kernel, single staged image: DCs come from this [hreal][wreal] array
 };
 
 // reference: src/effect.c:143-153 / 207-217
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(kThreads) k3_rewrite_kernel(const K3Params p, 
             Row8     row;
             row.w[0] = row.w[1] = row.w[2] = row.w[3] = 0;
             if(r == 0) {
-                int dc = first_is_zero ? 0 : (int)bp[0];
+                int dc = first_is_zero ? 0 : (p.dc_compact ? (int)p.dc_compact[(size_t)l * wreal + k] : (int)bp[0]);
                 dc = fold_dc(p, dc, q0);
                 row.w[0] = (uint32_t)dc & 0xffffu;
             }
@@ -92,13 +93,37 @@ __global__ void __launch_bounds__(kThreads) k3_dc_kernel(const K3Params p) {
     }
 }
 
+// DC-only pipeline on a COMPACT array of DC values (one int16 per block): what the host-pointer entry point
+// stages for one image whose planes live in pageable host memory -- 2 bytes per block cross PCIe instead of 128
+__global__ void __launch_bounds__(kThreads) k3_dc_compact_kernel(const K3Params p, int16_t *dc, int nblk, int q0) {
+    for(int i = blockIdx.x * kThreads + threadIdx.x; i < nblk; i += gridDim.x * kThreads) dc[i] = (int16_t)fold_dc(p, (int)dc[i], q0);
+}
+
+cudaError_t launch_k3_dc_compact(cudaStream_t s, int16_t *dc_dev, int nblk, int q0, int comp, const mjx_effect_op_t *ops, int nops) {
+    K3Params p{};
+    p.comp = comp;
+    for(int i = 0; i < nops; i++) {
+        if(ops[i].comp != comp) continue;
+        if(p.nops == kMaxOps) return cudaErrorInvalidValue;
+        p.op[p.nops] = ops[i].op;
+        p.value[p.nops] = ops[i].value;
+        p.nops++;
+    }
+    if(p.nops == 0 || nblk <= 0) return cudaSuccess;
+    int grid = (nblk + kThreads - 1) / kThreads;
+    if(grid > 148 * 8) grid = 148 * 8;
+    k3_dc_compact_kernel<<<grid, kThreads, 0, s>>>(p, dc_dev, nblk, q0);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_k3(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, int ncomp, const mjx_effect_op_t *ops,
-                      int nops, int *launches) {
+                      int nops, int *launches, const int16_t *const *dc_compact) {
     if(n <= 0) return cudaSuccess;
     for(int c = 0; c < ncomp; c++) {
         K3Params p{};
         p.items = items_dev;
         p.comp = c;
+        p.dc_compact = (dc_compact && n == 1) ? dc_compact[c] : nullptr;
         bool rewrite = false;
         for(int i = 0; i < nops; i++) {
             if(ops[i].comp != c) continue;

@@ -782,18 +782,72 @@ int mjx_effects_rows_host(mjx_ctx *ctx, int ncomp, int16_t *const *const *rows, 
         if(!used[c]) need_read[c] = ops[i].op != MJX_FX_ZERO; // a leading ZERO makes the old content irrelevant
         used[c] = true;
     }
-    size_t off[MJX_MAX_COMPONENTS], total = align_up(sizeof(mjx_image_desc_t), 256);
+    bool dc_only = nops > 0;
+    for(int i = 0; i < nops; i++) dc_only = dc_only && ops[i].op == MJX_FX_ADD_DC;
+    if(dc_only) {
+        // tint / luminance: only the DC of every block is read and written, so only the DCs are staged -- the host
+        // gathers them (one strided pass over the rows, like the reference's own loop), 2 bytes per block cross PCIe
+        size_t doff[MJX_MAX_COMPONENTS], dtotal = 0;
+        for(int c = 0; c < ncomp; c++) {
+            if(!used[c]) continue;
+            if(!rows[c] || !q[c] || wreal[c] < 0 || hreal[c] < 0) return MJX_ERR_ARG;
+            doff[c] = dtotal;
+            dtotal = align_up(dtotal + (size_t)wreal[c] * hreal[c] * sizeof(int16_t), 256);
+        }
+        if(dtotal == 0) return MJX_OK;
+        if((rv = ensure_pin(ctx, dtotal)) || (rv = ensure_dev(ctx, dtotal))) return rv;
+        char *pin = (char *)ctx->pin, *dev = (char *)ctx->dev;
+        for(int c = 0; c < ncomp; c++) {
+            if(!used[c]) continue;
+            int16_t *dst = (int16_t *)(pin + doff[c]);
+            for(int l = 0; l < hreal[c]; l++) {
+                if(!rows[c][l]) return MJX_ERR_ARG;
+                const int16_t *row = rows[c][l];
+                for(int k = 0; k < wreal[c]; k++) dst[(size_t)l * wreal[c] + k] = row[(size_t)k * 64];
+            }
+        }
+        MJX_CUDA(ctx, cudaMemcpyAsync(dev, pin, dtotal, cudaMemcpyHostToDevice, ctx->stream));
+        for(int c = 0; c < ncomp; c++) {
+            if(!used[c]) continue;
+            cudaError_t e = launch_k3_dc_compact(ctx->stream, (int16_t *)(dev + doff[c]), wreal[c] * hreal[c], (int)q[c][0], c, ops, nops);
+            ctx->launches++;
+            if(e != cudaSuccess) return fail(ctx, e, "k3 effects kernel");
+        }
+        MJX_CUDA(ctx, cudaMemcpyAsync(pin, dev, dtotal, cudaMemcpyDeviceToHost, ctx->stream));
+        MJX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for(int c = 0; c < ncomp; c++) {
+            if(!used[c]) continue;
+            const int16_t *src = (const int16_t *)(pin + doff[c]);
+            for(int l = 0; l < hreal[c]; l++) {
+                int16_t *row = rows[c][l];
+                for(int k = 0; k < wreal[c]; k++) row[(size_t)k * 64] = src[(size_t)l * wreal[c] + k];
+            }
+        }
+        return MJX_OK;
+    }
+    // Rewrite pipelines (a ZERO or PIXELATE step): every AC coefficient ends as 0, so the only input a component can
+    // still need is its DCs (PIXELATE first) -- those are gathered compactly (2 bytes per block up); the whole
+    // planes come back (128 bytes per block down).  A component's list that contains no such step but ADD_DCs only
+    // cannot occur here together with a rewrite of another component in the reference's API; it is handled by
+    // staging its rows fully.
+    bool   rewrites[MJX_MAX_COMPONENTS] = {};
+    for(int i = 0; i < nops; i++)
+        if(ops[i].op == MJX_FX_ZERO || ops[i].op == MJX_FX_PIXELATE) rewrites[ops[i].comp] = true;
+    size_t off[MJX_MAX_COMPONENTS], dcoff[MJX_MAX_COMPONENTS], total = align_up(sizeof(mjx_image_desc_t), 256);
     for(int c = 0; c < ncomp; c++) {
         if(!used[c]) continue;
         if(!rows[c] || !q[c] || wreal[c] < 0 || hreal[c] < 0) return MJX_ERR_ARG;
         off[c] = total;
         total = align_up(total + (size_t)wreal[c] * hreal[c] * 128, 256);
+        dcoff[c] = total;
+        if(rewrites[c] && need_read[c]) total = align_up(total + (size_t)wreal[c] * hreal[c] * sizeof(int16_t), 256);
     }
     if((rv = ensure_pin(ctx, total)) || (rv = ensure_dev(ctx, total))) return rv;
     char             *pin = (char *)ctx->pin, *dev = (char *)ctx->dev;
     mjx_image_desc_t *desc = (mjx_image_desc_t *)pin;
     memset(desc, 0, sizeof(*desc));
-    const size_t head = align_up(sizeof(mjx_image_desc_t), 256);
+    const size_t   head = align_up(sizeof(mjx_image_desc_t), 256);
+    const int16_t *dc_dev[MJX_MAX_COMPONENTS] = {};
     for(int c = 0; c < ncomp; c++) {
         if(!used[c]) continue;
         desc->plane[c] = (uint64_t)(uintptr_t)(dev + off[c]);
@@ -802,15 +856,28 @@ int mjx_effects_rows_host(mjx_ctx *ctx, int ncomp, int16_t *const *const *rows, 
         desc->wreal[c] = wreal[c];
         desc->hreal[c] = hreal[c];
         memcpy(desc->q[c], q[c], 128);
-        if(need_read[c])
+        if(!need_read[c]) continue;
+        for(int l = 0; l < hreal[c]; l++)
+            if(!rows[c][l]) return MJX_ERR_ARG;
+        if(rewrites[c]) { // DCs only
+            int16_t *dst = (int16_t *)(pin + dcoff[c]);
+            for(int l = 0; l < hreal[c]; l++)
+                for(int k = 0; k < wreal[c]; k++) dst[(size_t)l * wreal[c] + k] = rows[c][l][(size_t)k * 64];
+            dc_dev[c] = (const int16_t *)(dev + dcoff[c]);
+        }
+        else
             for(int l = 0; l < hreal[c]; l++) memcpy(pin + off[c] + (size_t)l * wreal[c] * 128, rows[c][l], (size_t)wreal[c] * 128);
     }
     MJX_CUDA(ctx, cudaMemcpyAsync(dev, pin, head, cudaMemcpyHostToDevice, ctx->stream));
-    for(int c = 0; c < ncomp; c++)
-        if(used[c] && need_read[c])
+    for(int c = 0; c < ncomp; c++) {
+        if(!used[c] || !need_read[c]) continue;
+        if(rewrites[c])
+            MJX_CUDA(ctx, cudaMemcpyAsync(dev + dcoff[c], pin + dcoff[c], (size_t)wreal[c] * hreal[c] * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+        else
             MJX_CUDA(ctx, cudaMemcpyAsync(dev + off[c], pin + off[c], (size_t)wreal[c] * hreal[c] * 128, cudaMemcpyHostToDevice, ctx->stream));
+    }
     int         launches = 0;
-    cudaError_t e = launch_k3(ctx->stream, (const mjx_image_desc_t *)dev, 1, ncomp, ops, nops, &launches);
+    cudaError_t e = launch_k3(ctx->stream, (const mjx_image_desc_t *)dev, 1, ncomp, ops, nops, &launches, dc_dev);
     ctx->launches += launches;
     if(e != cudaSuccess) return fail(ctx, e, "k3 effects kernel");
     for(int c = 0; c < ncomp; c++)

@@ -114,8 +114,11 @@ cudaError_t launch_count_classes(cudaStream_t s, const mjx_dropon *d, unsigned l
 cudaError_t launch_build_lists(cudaStream_t s, mjx_dropon *d, uint32_t *chunk_counts_dev, int *launches);
 cudaError_t launch_k2(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, const DropView &view, int block_x,
                       int block_y, void *scratch, int strict, int sm_count, int class_mask, int *launches);
+// dc_compact (optional, n == 1): per component a device array [hreal][wreal] the rewrite kernel takes the DCs from
 cudaError_t launch_k3(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, int ncomp, const mjx_effect_op_t *ops,
-                      int nops, int *launches);
+                      int nops, int *launches, const int16_t *const *dc_compact = nullptr);
+// DC-only step list of component `comp` on a compact device array of nblk DC values
+cudaError_t launch_k3_dc_compact(cudaStream_t s, int16_t *dc_dev, int nblk, int q0, int comp, const mjx_effect_op_t *ops, int nops);
 
 } // namespace mjx
 
