@@ -108,6 +108,9 @@ int         mjx_ctx_set_strict(mjx_ctx *ctx, int strict);
 /* on = 1 (default): mjx_compose_batch_host runs K2 directly on page-locked (GPU-addressable) host planes, so only
  * the blocks the dropon touches cross PCIe; 0: always stage the region under the dropon through device memory */
 int         mjx_ctx_set_zero_copy(mjx_ctx *ctx, int on);
+/* device self-test: K2's per-image reciprocal tables (MUFU.RCP based) give trunc(a / q) exactly for every q in
+ * [1, 65535] and every |a| <= 2^17; *mismatches receives the number of (a, q) pairs that do not (expected 0) */
+int         mjx_selftest_reciprocal(mjx_ctx *ctx, long long *mismatches);
 /* profiling aid: which fast-path K2 kernels run -- bit 0 the OPAQUE/U kernel, bit 1 the G kernel (default 3 = both) */
 int         mjx_ctx_set_class_mask(mjx_ctx *ctx, int mask);
 void       *mjx_ctx_stream(mjx_ctx *ctx);

@@ -129,6 +129,7 @@ def load_mjx() -> C.CDLL:
     L.mjx_dropon_generic_slots.argtypes = [vp]
     L.mjx_ctx_set_zero_copy.argtypes = [vp, C.c_int]
     L.mjx_ctx_set_class_mask.argtypes = [vp, C.c_int]
+    L.mjx_selftest_reciprocal.argtypes = [vp, C.POINTER(C.c_longlong)]
     L.mjx_compose_batch_device.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int]
     L.mjx_compose_batch_host.argtypes = [vp, C.POINTER(HostImage), C.c_int, vp, C.c_int, C.c_int]
     L.mjx_compose_rows_host.argtypes = [vp, C.c_int, vp, vp, vp]
@@ -241,6 +242,12 @@ class Engine:
     def set_zero_copy(self, on: bool) -> None:
         """on (default): compose_batch_host runs K2 directly on page-locked host planes; off: always stage"""
         self._check(self.lib.mjx_ctx_set_zero_copy(self.ctx, 1 if on else 0), "mjx_ctx_set_zero_copy")
+
+    def selftest_reciprocal(self) -> int:
+        """exhaustive device check of K2's reciprocal tables; returns the number of mismatching (a, q) pairs"""
+        n = C.c_longlong(-1)
+        self._check(self.lib.mjx_selftest_reciprocal(self.ctx, C.byref(n)), "mjx_selftest_reciprocal")
+        return n.value
 
     def set_class_mask(self, mask: int) -> None:
         """profiling aid: bit 0 = OPAQUE/U kernel, bit 1 = G kernel of the fast K2 path (default 3)"""

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kThreads) k2_simple_kernel(const FastParams p)
     for(int k = threadIdx.x; k < ni * 64; k += kThreads) {
         const float q = fmaxf((float)p.items[i0 + (k >> 6)].q[c][k & 63], 1.0f);
         s_q[k >> 6][k & 63] = q;
-        s_rq[k >> 6][k & 63] = quant_rcp_f(q);
+        s_rq[k >> 6][k & 63] = quant_rcp_fast(q);
     }
 
     const uint32_t  e = __ldg(p.drop.list_simple + tile * 32 + t);
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(kGWarps * 32, kMinCtas) k2_generic_kernel(cons
                 const float    q0 = fmaxf((float)(qw & 0xffffu), 1.0f), q1 = fmaxf((float)(qw >> 16), 1.0f);
                 *reinterpret_cast<float2 *>(tab + 2 * lane) = make_float2(q0 * pre0, q1 * pre1);
                 *reinterpret_cast<float2 *>(tab + 64 + 2 * lane) = make_float2(q0, q1);
-                *reinterpret_cast<float2 *>(tab + 128 + 2 * lane) = make_float2(quant_rcp_f(q0), quant_rcp_f(q1));
+                *reinterpret_cast<float2 *>(tab + 128 + 2 * lane) = make_float2(quant_rcp_fast(q0), quant_rcp_fast(q1));
             }
             __syncwarp();
 
@@ -483,6 +483,34 @@ __global__ void __launch_bounds__(kGWarps * 32, kMinCtas) k2_generic_kernel(cons
         }
         cp_async_wait<0>();
     }
+}
+
+// =========================================================================================
+// self-test: the MUFU-based reciprocal tables divide exactly
+// =========================================================================================
+
+// one CTA per quantiser value q; its threads sweep a = -2^17 .. 2^17 in pairs through tdiv_pair()
+__global__ void __launch_bounds__(256) selftest_reciprocal_kernel(unsigned long long *mismatches, int q_first) {
+    const int   q = q_first + blockIdx.x;
+    const float rq = quant_rcp_fast((float)q);
+    unsigned    bad = 0;
+    for(int a = -(1 << 17) + 2 * threadIdx.x; a <= (1 << 17); a += 2 * 256) {
+        const int      b = a + 1 <= (1 << 17) ? a + 1 : a;
+        const uint32_t pk = tdiv_pair(f2((float)a, (float)b), f2(rq, rq));
+        bad += (int16_t)(pk & 0xffffu) != (int16_t)(a / q);
+        bad += (int16_t)(pk >> 16) != (int16_t)(b / q);
+    }
+    if(bad) atomicAdd(mismatches, (unsigned long long)bad);
+}
+
+cudaError_t launch_selftest_reciprocal(cudaStream_t s, unsigned long long *mismatches_dev) {
+    for(int q0 = 1; q0 <= 65535; q0 += 32768) {
+        const int cnt = 65535 - q0 + 1 < 32768 ? 65535 - q0 + 1 : 32768;
+        selftest_reciprocal_kernel<<<cnt, 256, 0, s>>>(mismatches_dev, q0);
+        cudaError_t e = cudaGetLastError();
+        if(e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 // =========================================================================================

@@ -535,6 +535,22 @@ int mjx_dropon_download_generic(mjx_ctx *ctx, const mjx_dropon *d, uint32_t *lis
     return MJX_OK;
 }
 
+int mjx_selftest_reciprocal(mjx_ctx *ctx, long long *mismatches) {
+    int rv = use_device(ctx);
+    if(rv) return rv;
+    if(!mismatches) return MJX_ERR_ARG;
+    if((rv = ensure_scratch(ctx, 1024)) != MJX_OK) return rv;
+    unsigned long long *cnt = reinterpret_cast<unsigned long long *>((char *)ctx->scratch + 512), h = 0;
+    MJX_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(h), ctx->stream));
+    cudaError_t e = launch_selftest_reciprocal(ctx->stream, cnt);
+    ctx->launches += 2;
+    if(e != cudaSuccess) return fail(ctx, e, "selftest_reciprocal_kernel");
+    MJX_CUDA(ctx, cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    MJX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *mismatches = (long long)h;
+    return MJX_OK;
+}
+
 int mjx_ctx_set_class_mask(mjx_ctx *ctx, int mask) {
     if(!ctx) return MJX_ERR_ARG;
     ctx->class_mask = mask & 3;

@@ -117,6 +117,7 @@ cudaError_t launch_k2(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, 
 // dc_compact (optional, n == 1): per component a device array [hreal][wreal] the rewrite kernel takes the DCs from
 cudaError_t launch_k3(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, int ncomp, const mjx_effect_op_t *ops,
                       int nops, int *launches, const int16_t *const *dc_compact = nullptr);
+cudaError_t launch_selftest_reciprocal(cudaStream_t s, unsigned long long *mismatches_dev);
 // DC-only step list of component `comp` on a compact device array of nblk DC values
 cudaError_t launch_k3_dc_compact(cudaStream_t s, int16_t *dc_dev, int nblk, int q0, int comp, const mjx_effect_op_t *ops, int nops);
 

@@ -595,3 +595,9 @@ def test_compose_batch_pipeline_equals_per_image_api(engine):
         j = M.Jpeg()
         assert j.read_jpeg_from_memory(src) == 0
         assert j.write_jpeg_to_memory(0)[1] == o
+
+
+def test_reciprocal_tables_divide_exactly_on_device(engine):
+    """K2 builds its per-image 1/q tables with MUFU.RCP; trunc(a * rq) must equal a / q for every 16-bit quantiser
+    value and every dequantised magnitude the fast path can see -- checked exhaustively by a device kernel"""
+    assert engine.selftest_reciprocal() == 0
