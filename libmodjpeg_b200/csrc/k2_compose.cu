@@ -379,6 +379,7 @@ __global__ void __launch_bounds__(kGWarps * 32, kMinCtas) k2_generic_kernel(cons
             unsigned long long       a = 0;
             if(my_valid && my_row < rows && my_col < stride) a = plane + ((unsigned long long)my_row * stride + my_col) * 128ull;
             addr[lane] = a;
+            const bool all_there = __all_sync(0xffffffffu, a != 0); // the usual case: every block of the tile lies on this image
             __syncwarp();
             // lane -> chunk (lane & 7) of blocks (lane >> 3) + 4j
             const unsigned            dst = ws32 + st * kStageBytes + (lane >> 3) * kInStride + (lane & 7) * 16;
@@ -387,9 +388,15 @@ __global__ void __launch_bounds__(kGWarps * 32, kMinCtas) k2_generic_kernel(cons
             unsigned long long        b[8];
 #pragma unroll
             for(int j = 0; j < 8; j++) b[j] = ap[4 * j];
+            if(all_there) {
 #pragma unroll
-            for(int j = 0; j < 8; j++)
-                cp_async16(dst + j * 4 * kInStride, reinterpret_cast<const void *>((b[j] ? b[j] : (unsigned long long)(uintptr_t)p.items) + coff), b[j] ? 16u : 0u);
+                for(int j = 0; j < 8; j++) cp_async16(dst + j * 4 * kInStride, reinterpret_cast<const void *>(b[j] + coff));
+            }
+            else {
+#pragma unroll
+                for(int j = 0; j < 8; j++)
+                    cp_async16(dst + j * 4 * kInStride, reinterpret_cast<const void *>((b[j] ? b[j] : (unsigned long long)(uintptr_t)p.items) + coff), b[j] ? 16u : 0u);
+            }
             if(lane < 8) cp_async16(ws32 + st * kStageBytes + kInBytes + lane * 16, reinterpret_cast<const char *>(&p.items[i0 + k * kGWarps].q[tile_c][0]) + lane * 16);
         };
 
