@@ -164,6 +164,46 @@ def test_k2_device_batch_vs_oracle(engine, port, subs, gray, quality):
     print("\nK2 parity", subs, "gray" if gray else "", f"q{quality}:", report)
 
 
+def test_k2_device_batch_mixed_quant_tables(engine, port):
+    """one launch over images that all carry DIFFERENT quantisation tables (qualities 35..97), more images than a
+    warp handles per work item: the per-image table path of both K2 kernels"""
+    from libmodjpeg_b200 import Layout
+    from libmodjpeg_b200.batch import DeviceBatch
+
+    W_, H_ = 208, 144
+    quals = [35 + 2 * i for i in range(32)] * 4 + [50, 75]  # 130 images > 96 per item: two chunks per tile
+    base = {q: _decode(util.jpeg_bytes(W_, H_, "420", q, seed=500 + q)) for q in sorted(set(quals))}
+    dec = [base[q] for q in quals]
+    info, samp = dec[0][1], dec[0][2]
+    shapes = [p.shape[:2] for p in dec[0][3]]
+    raw = util.logo_rgba(160, 112, 64, 27)
+    i3, a3, scs, sblend = util.ingest_raw(raw, 2, 255)
+    batch = DeviceBatch(engine, shapes, len(dec))
+    batch.set_descs(np.stack([np.stack(d[4]) for d in dec]))
+    want = {}
+    g = None
+    for q, (j, inf, sp, planes, qt) in base.items():
+        exp = [p.copy() for p in planes]
+        rv, g, D, Wc = util.oracle_compose(port, exp, qt, inf["width"], inf["height"], inf["colorspace"], sp, i3, a3, scs, sblend, 16, 3, -2)
+        assert rv == 0 and g["visible"]
+        want[q] = exp
+    for i, d in enumerate(dec):
+        batch.upload_image(i, d[3])
+    cd = engine.dropon_compile(i3, a3, scs, Layout.make(info["colorspace"], samp), (g["blockoffset_x"], g["blockoffset_y"]),
+                               (g["crop_x"], g["crop_y"], g["crop_w"], g["crop_h"]))
+    cls_maps = [cd.download(c)[2] for c in range(info["ncomp"])]
+    engine.compose_batch_device(batch.descs_dev, batch.n, cd, g["block_x"], g["block_y"])
+    engine.sync()
+    nG = nbad = 0
+    for i, q in enumerate(quals):
+        a, b = _check_planes(batch.download_image(i), want[q], base[q][3], cls_maps, (g["block_x"], g["block_y"]), samp, ("mixedq", q, i))
+        nG += a
+        nbad += b
+    print(f"\nK2 mixed quant tables: {len(quals)} images, {nG} generic coefficients, {nbad} differ by one step")
+    cd.free()
+    batch.free()
+
+
 def test_k2_with_oracle_compiled_dropon(engine, port):
     """K2 in isolation: the dropon coefficients come from the oracle (mjx_dropon_from_coefficients)"""
     from libmodjpeg_b200 import Layout
