@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kThreads) k2_simple_kernel(const FastParams p)
 }
 
 // =========================================================================================
-// fast path, kernel 3: G blocks -- thread per block, packed fp32 (FADD2 / FMUL2 / FFMA2)
+// fast path, kernel 2: G blocks -- thread per block, packed fp32 (FADD2 / FMUL2 / FFMA2)
 // =========================================================================================
 //
 // Work item = (tile of 32 list entries of ONE component, chunk of images).  A CTA of 4 warps
@@ -247,8 +247,8 @@ __global__ void __launch_bounds__(kThreads) k2_simple_kernel(const FastParams p)
 //            writes the 32 blocks back with coalesced 128-bit stores.
 //
 // The two pairings make every 1-D pass a pure SIMD2 computation; switching pairing costs 8 extra
-// scalar adds per pass instead of a register transpose.  ~1.4 k issue slots per block (the
-// scalar fp32 version needed ~2.3 k), which moves the class from issue-bound to HBM-bound.
+// scalar adds per pass instead of a register transpose.  ~1.5 k issue slots per block (the
+// scalar fp32 version needed ~2.3 k); measured balance and what limits it: DESIGN.md 4.2.
 
 static constexpr int kGStages = 2;
 // Shared-memory blocks are PADDED by one 16-byte chunk (stride 144 B for int16 blocks, 272 B for
