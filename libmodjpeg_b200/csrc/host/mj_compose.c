@@ -7,8 +7,87 @@
  */
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "mj_private.h"
+
+/*
+ * Compiled-dropon cache (opt-in: MJX_DROPON_CACHE=1 in the environment).  The reference compiles the dropon again on
+ * every mj_compose (src/compose.c:155-177); a server that puts ONE logo on many images pays K1 + the pixel upload per
+ * call for nothing.  With the cache on, the calling thread keeps its last few compiled dropons keyed by everything the
+ * compile depends on: the dropon's buffers and dimensions, the target layout and the placement remainder.  The key
+ * holds the buffer ADDRESSES, not their content, so the contract is: do not edit d->image / d->alpha in place after
+ * mj_read_dropon_* (re-reading or freeing a dropon is fine: mj_free_dropon bumps the generation below).
+ */
+#define MJ_CACHE_SLOTS 4
+typedef struct {
+    const void    *image, *alpha;
+    int            width, height, colorspace, blend;
+    unsigned long  generation;
+    mjx_layout_t   layout;
+    mjx_geometry_t g; /* only the fields the compile uses are compared */
+    mjx_dropon    *cd;
+    unsigned long  last_use;
+} cache_slot_t;
+
+static __thread cache_slot_t  t_cache[MJ_CACHE_SLOTS];
+static __thread unsigned long t_clock;
+unsigned long                 mjp_dropon_generation = 1; /* bumped by mj_free_dropon / mj_read_dropon_* (mj_dropon.c) */
+
+static int cache_enabled(void) {
+    static int on = -1;
+    if(on < 0) {
+        const char *e = getenv("MJX_DROPON_CACHE");
+        on = (e != NULL && atoi(e) == 1) ? 1 : 0;
+    }
+    return on;
+}
+
+static int slot_matches(const cache_slot_t *s, const mj_dropon_t *d, const mjx_layout_t *L, const mjx_geometry_t *g) {
+    return s->cd != NULL && s->image == d->image && s->alpha == d->alpha && s->width == d->width && s->height == d->height &&
+           s->colorspace == d->colorspace && s->blend == d->blend && s->generation == __atomic_load_n(&mjp_dropon_generation, __ATOMIC_RELAXED) &&
+           memcmp(&s->layout, L, sizeof(*L)) == 0 && s->g.blockoffset_x == g->blockoffset_x && s->g.blockoffset_y == g->blockoffset_y &&
+           s->g.crop_x == g->crop_x && s->g.crop_y == g->crop_y && s->g.crop_w == g->crop_w && s->g.crop_h == g->crop_h;
+}
+
+/* called when the calling thread's engine context goes away (mj_device.c) */
+void mjp_compose_cache_clear(void) {
+    for(int i = 0; i < MJ_CACHE_SLOTS; i++) {
+        if(t_cache[i].cd != NULL) mjx_dropon_free(t_cache[i].cd);
+        memset(&t_cache[i], 0, sizeof(t_cache[i]));
+    }
+}
+
+/* returns a compiled dropon for (d, layout, g): from the cache, or freshly compiled (and cached when enabled);
+ * *owned = 1 when the caller has to free it */
+static int get_compiled(mjx_ctx *ctx, mj_dropon_t *d, const mjx_layout_t *L, const mjx_geometry_t *g, mjx_dropon **out, int *owned) {
+    *owned = 1;
+    if(cache_enabled()) {
+        for(int i = 0; i < MJ_CACHE_SLOTS; i++)
+            if(slot_matches(&t_cache[i], d, L, g)) {
+                t_cache[i].last_use = ++t_clock;
+                *out = t_cache[i].cd;
+                *owned = 0;
+                return MJX_OK;
+            }
+    }
+    int rv = mjx_dropon_compile(ctx, out, d->image, d->alpha, d->width, d->height, d->colorspace, L, g->blockoffset_x, g->blockoffset_y,
+                                g->crop_x, g->crop_y, g->crop_w, g->crop_h, 0);
+    if(rv != MJX_OK || !cache_enabled()) return rv;
+    int victim = 0;
+    for(int i = 1; i < MJ_CACHE_SLOTS; i++)
+        if(t_cache[i].cd == NULL || (t_cache[victim].cd != NULL && t_cache[i].last_use < t_cache[victim].last_use)) victim = i;
+    if(t_cache[victim].cd != NULL) mjx_dropon_free(t_cache[victim].cd);
+    cache_slot_t *s = &t_cache[victim];
+    s->image = d->image, s->alpha = d->alpha, s->width = d->width, s->height = d->height, s->colorspace = d->colorspace, s->blend = d->blend;
+    s->generation = __atomic_load_n(&mjp_dropon_generation, __ATOMIC_RELAXED);
+    s->layout = *L;
+    s->g = *g;
+    s->cd = *out;
+    s->last_use = ++t_clock;
+    *owned = 0;
+    return MJX_OK;
+}
 
 int mj_compose(mj_jpeg_t *m, mj_dropon_t *d, unsigned int align, int offset_x, int offset_y) {
     if(m == NULL || d == NULL) return MJ_ERR_NULL_DATA;
@@ -27,8 +106,8 @@ int mj_compose(mj_jpeg_t *m, mj_dropon_t *d, unsigned int align, int offset_x, i
     if(ctx == NULL) return MJ_ERR_DEVICE;
 
     mjx_dropon *cd = NULL;
-    rv = mjx_dropon_compile(ctx, &cd, d->image, d->alpha, d->width, d->height, d->colorspace, &layout, g.blockoffset_x,
-                            g.blockoffset_y, g.crop_x, g.crop_y, g.crop_w, g.crop_h, 0);
+    int         cd_owned = 1;
+    rv = get_compiled(ctx, d, &layout, &g, &cd, &cd_owned);
     if(rv != MJX_OK) {
         if(rv == MJX_ERR_UNSUPPORTED) fprintf(stderr, "Unsupported color conversion request\n"); /* libjpeg's words, as the reference prints them */
         else if(rv == MJX_ERR_DEVICE) fprintf(stderr, "libmodjpeg (B200): %s\n", mjx_ctx_last_error(ctx));
@@ -76,6 +155,6 @@ int mj_compose(mj_jpeg_t *m, mj_dropon_t *d, unsigned int align, int offset_x, i
 done:
     trap->armed = 0;
     for(int c = 0; c < MJX_MAX_COMPONENTS; c++) free(rows[c]);
-    mjx_dropon_free(cd);
+    if(cd_owned) mjx_dropon_free(cd);
     return result;
 }

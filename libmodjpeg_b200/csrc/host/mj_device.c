@@ -13,7 +13,10 @@
 static pthread_key_t  g_key;
 static pthread_once_t g_once = PTHREAD_ONCE_INIT;
 
-static void ctx_destructor(void *p) { mjx_ctx_destroy((mjx_ctx *)p); }
+static void ctx_destructor(void *p) {
+    mjp_compose_cache_clear(); /* compiled dropons cached by this thread's mj_compose calls */
+    mjx_ctx_destroy((mjx_ctx *)p);
+}
 static void make_key(void) { pthread_key_create(&g_key, ctx_destructor); }
 
 mjx_ctx *mjx_host_ctx(void) {

@@ -18,8 +18,11 @@ void mj_init_dropon(mj_dropon_t *d) {
     if(d != NULL) memset(d, 0, sizeof(*d));
 }
 
+extern unsigned long mjp_dropon_generation; /* mj_compose.c: invalidates cached compiled dropons */
+
 void mj_free_dropon(mj_dropon_t *d) {
     if(d == NULL) return;
+    if(d->image != NULL || d->alpha != NULL) __atomic_add_fetch(&mjp_dropon_generation, 1, __ATOMIC_RELAXED);
     free(d->image);
     free(d->alpha);
     mj_init_dropon(d);

@@ -56,6 +56,9 @@ int mjp_decode_to_raw(unsigned char **raw, int *width, int *height, int want_col
 
 int mjp_read_whole_file(unsigned char **buffer, size_t *len, const char *filename);
 
+/* frees the calling thread's cached compiled dropons (mj_compose.c, MJX_DROPON_CACHE=1) */
+void mjp_compose_cache_clear(void);
+
 /* MJX_* -> MJ_* */
 int mjp_map_error(int mjx_rv);
 

@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(256) selftest_reciprocal_kernel(unsigned long 
     const int   q = q_first + blockIdx.x;
     const float rq = quant_rcp_fast((float)q);
     unsigned    bad = 0;
-    for(int a = -(1 << 17) + 2 * threadIdx.x; a <= (1 << 17); a += 2 * 256) {
+    for(int a = -(1 << 17) + 2 * (int)threadIdx.x; a <= (1 << 17); a += 2 * 256) {
         const int      b = a + 1 <= (1 << 17) ? a + 1 : a;
         const uint32_t pk = tdiv_pair(f2((float)a, (float)b), f2(rq, rq));
         bad += (int16_t)(pk & 0xffffu) != (int16_t)(a / q);

@@ -11,6 +11,8 @@ import pytest
 
 import util
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 pytestmark = pytest.mark.gpu
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -641,3 +643,47 @@ def test_reciprocal_tables_divide_exactly_on_device(engine):
     """K2 builds its per-image 1/q tables with MUFU.RCP; trunc(a * rq) must equal a / q for every 16-bit quantiser
     value and every dequantised magnitude the fast path can see -- checked exhaustively by a device kernel"""
     assert engine.selftest_reciprocal() == 0
+
+
+def test_compiled_dropon_cache_opt_in(engine, tmp_path):
+    """MJX_DROPON_CACHE=1: repeated mj_compose calls with one dropon reuse the compiled dropon (fewer kernel
+    launches), give identical results, and re-reading the dropon invalidates the entry"""
+    import subprocess
+    import sys
+
+    code = r'''
+import sys, ctypes, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import libmodjpeg_b200 as M, util
+from libmodjpeg_b200 import capi
+def launches():
+    return capi.load_mjx().mjx_ctx_kernel_launches(ctypes.c_void_p(capi.load_modjpeg().mjx_host_ctx()))
+raw = util.logo_rgba(96, 64, 32, 13)
+d = M.Dropon(); assert d.read_dropon_from_raw(raw, M.CS_RGBA, 255) == 0
+outs, per_call = [], []
+for i in range(4):
+    j = M.Jpeg(); assert j.read_jpeg_from_memory(util.jpeg_bytes(160, 128, "420", 85, seed=700)) == 0
+    l0 = launches() if i else 0
+    assert j.compose(d, M.ALIGN_CENTER, 0, 0) == 0
+    per_call.append(launches() - l0)
+    outs.append([p.copy() for p in j.planes()])
+assert all(np.array_equal(a, b) for o in outs[1:] for a, b in zip(o, outs[0]))
+raw2 = raw.copy(); raw2[:, :, 0] = 255 - raw2[:, :, 0]
+assert d.read_dropon_from_raw(raw2, M.CS_RGBA, 255) == 0      # new pixels: the cached entry must not be used
+j = M.Jpeg(); assert j.read_jpeg_from_memory(util.jpeg_bytes(160, 128, "420", 85, seed=700)) == 0
+assert j.compose(d, M.ALIGN_CENTER, 0, 0) == 0
+changed = any(not np.array_equal(a, b) for a, b in zip(j.planes(), outs[0]))
+print("RESULT", repr((per_call, changed)))
+''' % (ROOT, os.path.join(ROOT, "tests"))
+    env = dict(os.environ)
+    res = {}
+    for on in ("0", "1"):
+        env["MJX_DROPON_CACHE"] = on
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")][0]
+        res[on] = eval(line[len("RESULT"):])
+    (off_calls, off_changed), (on_calls, on_changed) = res["0"], res["1"]
+    assert off_changed and on_changed
+    assert off_calls[1] == off_calls[2] == off_calls[3]          # reference behaviour: recompile per call
+    assert on_calls[1] < off_calls[1] and on_calls[1] == on_calls[3]  # cached: only K2 launches remain
