@@ -568,7 +568,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
             "k2_simple_kernel": {"class": "OPAQUE+U", "launch_ms": ms_simple, "algorithmic_bytes": alg_simple,
                                  "achieved_gbs": alg_simple / (ms_simple * 1e-3) / 1e9 if ms_simple else None,
                                  "traffic": traffic.get("k2_simple_kernel"),
-                                 "note": "write-only on this workload; the box's write-only (memset) ceiling is ~3.9 TB/s (profiles/microbench/hbm_rw.txt)"},
+                                 "note": "write-only on this workload (cudaMemset reaches 3.9 TB/s on the same box, profiles/microbench/hbm_rw.txt)"},
         }
         dom = "k2_generic_kernel" if ms_generic >= ms_simple else "k2_simple_kernel"
         dom_gbs = kernels[dom]["achieved_gbs"] or 0.0
@@ -588,7 +588,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
                          "launch_ms": kernels[dom]["launch_ms"], "peak_source": peak_src,
                          "timing": "CUDA events on the launching stream around the kernel alone (other class group masked off), mean of the timed steps",
                          "step": {"achieved": achieved, "frac": achieved / peak, "algorithmic_bytes": alg_bytes, "ms": launch_ms,
-                                  "what": "whole K2 step = k2_simple_kernel + k2_generic_kernel back to back"},
+                                  "what": "whole K2 step = k2_generic_kernel with k2_simple_kernel beside it on a side stream (one small CTA per SM fits next to the G kernel's three), joined before the step ends"},
                          "kernels": kernels},
             "other_kernels": other,
             "e2e_files": files,

@@ -66,7 +66,8 @@ typedef struct {
     int block_x, block_y; /* origin on the image in MCUs */
 } mjx_geometry_t;
 
-/* one image of a device-resident batch; an array of these lives in device memory */
+/* one image of a device-resident batch; an array of these lives in device memory, 16-byte aligned (the kernels
+ * fetch the quantisation tables with 128-bit loads) */
 typedef struct {
     uint64_t plane[MJX_MAX_COMPONENTS];         /* device address of block (0,0) of each component plane */
     int32_t  stride_blocks[MJX_MAX_COMPONENTS]; /* blocks per plane row (libjpeg's virtual width) */
@@ -113,6 +114,9 @@ int         mjx_ctx_set_zero_copy(mjx_ctx *ctx, int on);
 int         mjx_selftest_reciprocal(mjx_ctx *ctx, long long *mismatches);
 /* profiling aid: which fast-path K2 kernels run -- bit 0 the OPAQUE/U kernel, bit 1 the G kernel (default 3 = both) */
 int         mjx_ctx_set_class_mask(mjx_ctx *ctx, int mask);
+/* 1 (default): batches of >= 64 images run the OPAQUE/U kernel beside the G kernel (a low-priority side stream of the
+ * ctx, joined back into the ctx stream before the call's work counts as done); 0: one after the other */
+int         mjx_ctx_set_overlap(mjx_ctx *ctx, int on);
 void       *mjx_ctx_stream(mjx_ctx *ctx);
 int         mjx_ctx_sync(mjx_ctx *ctx);
 const char *mjx_ctx_last_error(mjx_ctx *ctx);

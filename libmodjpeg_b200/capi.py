@@ -129,6 +129,7 @@ def load_mjx() -> C.CDLL:
     L.mjx_dropon_generic_slots.argtypes = [vp]
     L.mjx_ctx_set_zero_copy.argtypes = [vp, C.c_int]
     L.mjx_ctx_set_class_mask.argtypes = [vp, C.c_int]
+    L.mjx_ctx_set_overlap.argtypes = [vp, C.c_int]
     L.mjx_selftest_reciprocal.argtypes = [vp, C.POINTER(C.c_longlong)]
     L.mjx_compose_batch_device.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int]
     L.mjx_compose_batch_host.argtypes = [vp, C.POINTER(HostImage), C.c_int, vp, C.c_int, C.c_int]
@@ -252,6 +253,10 @@ class Engine:
     def set_class_mask(self, mask: int) -> None:
         """profiling aid: bit 0 = OPAQUE/U kernel, bit 1 = G kernel of the fast K2 path (default 3)"""
         self._check(self.lib.mjx_ctx_set_class_mask(self.ctx, mask), "mjx_ctx_set_class_mask")
+
+    def set_overlap(self, on: bool) -> None:
+        """large batches: OPAQUE/U kernel beside the G kernel (default) or one after the other"""
+        self._check(self.lib.mjx_ctx_set_overlap(self.ctx, 1 if on else 0), "mjx_ctx_set_overlap")
 
     def set_strict(self, strict: bool) -> None:
         """strict: one K2 kernel with the reference's int16 wrap-around (adversarial inputs); default fast kernels"""

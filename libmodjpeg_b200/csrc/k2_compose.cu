@@ -169,21 +169,33 @@ struct FastParams {
 
 static constexpr int kSimpleImages = 16; // images walked by one CTA of the simple kernel
 
-__global__ void __launch_bounds__(kThreads) k2_simple_kernel(const FastParams p) {
+// THREADS = 256: one CTA per tile.  THREADS = 128: two CTAs per tile, 64 registers x 128 threads -- small enough to sit
+// beside the three resident CTAs of the G kernel on every SM (10 240 registers are left there), which is how the two
+// kernels run concurrently (launch_k2).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k2_simple_kernel(const FastParams p) {
     __shared__ __align__(16) float s_q[kSimpleImages][64], s_rq[kSimpleImages][64];
-    const int r = threadIdx.x & 7, t = threadIdx.x >> 3;
-    const int tile = blockIdx.x;
+    constexpr int kPerTile = kThreads / THREADS; // CTAs per tile
+    const int     r = threadIdx.x & 7, t = (threadIdx.x >> 3) + (blockIdx.x % kPerTile) * (THREADS / 8);
+    const int     tile = blockIdx.x / kPerTile;
     int       c = 0; // tiles hold one component only
 #pragma unroll
     for(int i = 1; i < MJX_MAX_COMPONENTS; i++)
         if(i < p.drop.ncomp && tile >= p.drop.stile_start[i]) c = i;
     const int i0 = blockIdx.y * kSimpleImages, ni = min(p.n - i0, kSimpleImages);
 
-    // float tables of the chunk's images for this component: 16 x 64 entries, 4 per thread
-    for(int k = threadIdx.x; k < ni * 64; k += kThreads) {
-        const float q = fmaxf((float)p.items[i0 + (k >> 6)].q[c][k & 63], 1.0f);
-        s_q[k >> 6][k & 63] = q;
-        s_rq[k >> 6][k & 63] = quant_rcp_fast(q);
+    // float tables of the chunk's images for this component: one 128-bit load = 8 entries per thread, so that the
+    // CTA's start-up is one memory latency (it is exposed when a single small CTA runs beside the G kernel)
+    for(int k = threadIdx.x; k < ni * 8; k += THREADS) {
+        const uint4    w = __ldg(reinterpret_cast<const uint4 *>(&p.items[i0 + (k >> 3)].q[c][(k & 7) * 8]));
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+        float         *dq = &s_q[k >> 3][(k & 7) * 8], *drq = &s_rq[k >> 3][(k & 7) * 8];
+#pragma unroll
+        for(int j = 0; j < 4; j++) {
+            const float q0 = fmaxf((float)(ww[j] & 0xffffu), 1.0f), q1 = fmaxf((float)(ww[j] >> 16), 1.0f);
+            *reinterpret_cast<float2 *>(dq + 2 * j) = make_float2(q0, q1);
+            *reinterpret_cast<float2 *>(drq + 2 * j) = make_float2(quant_rcp_fast(q0), quant_rcp_fast(q1));
+        }
     }
 
     const uint32_t  e = __ldg(p.drop.list_simple + tile * 32 + t);
@@ -200,14 +212,25 @@ __global__ void __launch_bounds__(kThreads) k2_simple_kernel(const FastParams p)
 #pragma unroll
         for(int j = 0; j < 4; j++) D[j] = f2((float)row_get(dr, 2 * j), (float)row_get(dr, 2 * j + 1));
     }
+    // lane k of every warp fetches plane pointer / stride / rows of image k of the chunk; the per-image values are
+    // then broadcast by shuffle, so no global load sits on the per-image path (it matters when only one small CTA of
+    // this kernel is resident per SM, beside the G kernel)
+    const int          lane = threadIdx.x & 31;
+    unsigned long long d_plane = 0;
+    int                d_stride = 0, d_rows = 0;
+    if(lane < ni) {
+        const mjx_image_desc_t &im = p.items[i0 + lane];
+        d_plane = im.plane[c];
+        d_stride = im.stride_blocks[c];
+        d_rows = im.rows[c];
+    }
     __syncthreads();
-    if(!valid) return;
 
     for(int k = 0; k < ni; k++) {
-        const mjx_image_desc_t &im = p.items[i0 + k];
-        const int               stride = im.stride_blocks[c];
-        if(row >= im.rows[c] || col >= stride) continue;
-        int16_t      *ip = reinterpret_cast<int16_t *>(im.plane[c]) + ((size_t)row * stride + col) * 64 + r * 8;
+        const unsigned long long plane = __shfl_sync(0xffffffffu, d_plane, k);
+        const int                stride = __shfl_sync(0xffffffffu, d_stride, k), rows = __shfl_sync(0xffffffffu, d_rows, k);
+        if(!valid || row >= rows || col >= stride) continue;
+        int16_t      *ip = reinterpret_cast<int16_t *>(plane) + ((size_t)row * stride + col) * 64 + r * 8;
         const float4 ra = *reinterpret_cast<const float4 *>(&s_rq[k][r * 8]), rb = *reinterpret_cast<const float4 *>(&s_rq[k][r * 8 + 4]);
         Row8         out;
         if(opaque) { // trunc(D / q), the image block is not read
@@ -527,7 +550,7 @@ cudaError_t launch_selftest_reciprocal(cudaStream_t s, unsigned long long *misma
 size_t k2_scratch_bytes() { return 256; }
 
 cudaError_t launch_k2(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, const DropView &view, int block_x,
-                      int block_y, void *scratch, int strict, int sm_count, int class_mask, int *launches) {
+                      int block_y, void *scratch, int strict, int sm_count, int class_mask, int *launches, const K2Side *side) {
     if(n <= 0 || view.total_blocks <= 0) return cudaSuccess;
     cudaError_t e;
     if(strict) {
@@ -566,28 +589,53 @@ cudaError_t launch_k2(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, 
     p.block_y = block_y;
     p.images_per_item = n < 24 * g_warps ? n : 24 * g_warps; // per warp: <= 32 (one descriptor per lane); 16..32 measured within 1.5 %
 
-    if(view.n_simple > 0 && (class_mask & 1)) {
+    // Both classes present and a batch large enough to fill the machine: the two kernels run side by side.  The G kernel
+    // (fp32-pipe bound, ~45 % of HBM) is launched first and keeps its 3 CTAs per SM; the OPAQUE/U kernel (write bound)
+    // follows on the low-priority side stream in its 128-thread shape, one CTA of which fits into the registers the
+    // G kernel leaves free, and fills the idle issue slots and HBM bandwidth.
+    const bool both = view.n_simple > 0 && view.n_generic > 0 && (class_mask & 3) == 3;
+    const bool overlap = both && side && side->stream && n >= 64;
+    auto       launch_simple = [&](cudaStream_t st, bool small) -> cudaError_t {
         const unsigned tiles = (unsigned)(view.n_simple / 32);
         for(int first = 0; first < n; first += 65535 * kSimpleImages) {
             const int cnt = n - first < 65535 * kSimpleImages ? n - first : 65535 * kSimpleImages;
             FastParams q = p;
             q.items = items_dev + first;
             q.n = cnt;
-            k2_simple_kernel<<<dim3(tiles, (unsigned)((cnt + kSimpleImages - 1) / kSimpleImages)), kThreads, 0, s>>>(q);
-            if((e = cudaGetLastError()) != cudaSuccess) return e;
+            const unsigned gy = (unsigned)((cnt + kSimpleImages - 1) / kSimpleImages);
+            if(small) k2_simple_kernel<128><<<dim3(tiles * 2, gy), 128, 0, st>>>(q);
+            else k2_simple_kernel<kThreads><<<dim3(tiles, gy), kThreads, 0, st>>>(q);
+            const cudaError_t le = cudaGetLastError();
+            if(le != cudaSuccess) return le;
             if(launches) (*launches)++;
         }
-    }
-    if(view.n_generic > 0 && (class_mask & 2)) {
-        if((e = cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), s)) != cudaSuccess) return e;
+        return cudaSuccess;
+    };
+    auto launch_generic = [&]() -> cudaError_t {
+        cudaError_t ge;
+        if((ge = cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), s)) != cudaSuccess) return ge;
         const long long nitems = (long long)(view.n_generic / 32) * ((n + p.images_per_item - 1) / p.images_per_item);
         if(nitems > 0x7fffffffLL) return cudaErrorInvalidValue;
         const int sms = sm_count > 0 ? sm_count : 148;
         const int ctas = nitems < (long long)sms * ctas_per_sm ? (int)nitems : sms * ctas_per_sm;
         k2_generic_kernel<g_warps, 3><<<ctas, g_warps * 32, g_smem(g_warps), s>>>(p);
-        if((e = cudaGetLastError()) != cudaSuccess) return e;
+        if((ge = cudaGetLastError()) != cudaSuccess) return ge;
         if(launches) (*launches)++;
+        return cudaSuccess;
+    };
+    if(overlap) {
+        if((e = cudaEventRecord(side->fork, s)) != cudaSuccess) return e;
+        if((e = cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return e;
+        if((e = launch_generic()) != cudaSuccess) return e;
+        if((e = launch_simple(side->stream, true)) != cudaSuccess) return e;
+        if((e = cudaEventRecord(side->join, side->stream)) != cudaSuccess) return e;
+        if((e = cudaStreamWaitEvent(s, side->join, 0)) != cudaSuccess) return e;
+        return cudaSuccess;
     }
+    if(view.n_simple > 0 && (class_mask & 1))
+        if((e = launch_simple(s, false)) != cudaSuccess) return e;
+    if(view.n_generic > 0 && (class_mask & 2))
+        if((e = launch_generic()) != cudaSuccess) return e;
     return cudaSuccess;
 }
 

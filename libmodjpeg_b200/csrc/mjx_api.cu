@@ -82,6 +82,13 @@ int mjx_ctx_create(mjx_ctx **out, int device) {
     if(e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if(e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if(e == cudaSuccess) {
+        int lo = 0, hi = 0; // numerically larger = lower priority
+        e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if(e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, lo);
+        if(e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->side_fork, cudaEventDisableTiming);
+        if(e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->side_join, cudaEventDisableTiming);
+    }
+    if(e == cudaSuccess) {
         // compiled dropons come from the device's stream-ordered pool; keep freed blocks cached so that the
         // per-call compile of mj_compose (the reference recompiles per call too) never reaches the driver
         cudaMemPool_t pool;
@@ -97,6 +104,7 @@ int mjx_ctx_create(mjx_ctx **out, int device) {
         return MJX_ERR_DEVICE;
     }
     ctx->stream = ctx->own_stream;
+    if(const char *ev = getenv("MJX_K2_OVERLAP")) ctx->overlap = atoi(ev) != 0;
     *out = ctx;
     return MJX_OK;
 }
@@ -116,6 +124,12 @@ void mjx_ctx_destroy(mjx_ctx *ctx) {
     if(ctx->dev) cudaFree(ctx->dev);
     if(ctx->desc_dev) cudaFree(ctx->desc_dev);
     if(ctx->scratch) cudaFree(ctx->scratch);
+    if(ctx->side_stream) {
+        cudaStreamSynchronize(ctx->side_stream);
+        cudaStreamDestroy(ctx->side_stream);
+    }
+    if(ctx->side_fork) cudaEventDestroy(ctx->side_fork);
+    if(ctx->side_join) cudaEventDestroy(ctx->side_join);
     if(ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -557,6 +571,12 @@ int mjx_ctx_set_class_mask(mjx_ctx *ctx, int mask) {
     return MJX_OK;
 }
 
+int mjx_ctx_set_overlap(mjx_ctx *ctx, int on) {
+    if(!ctx) return MJX_ERR_ARG;
+    ctx->overlap = on ? 1 : 0;
+    return MJX_OK;
+}
+
 int mjx_ctx_set_zero_copy(mjx_ctx *ctx, int on) {
     if(!ctx) return MJX_ERR_ARG;
     ctx->zero_copy = on ? 1 : 0;
@@ -581,7 +601,9 @@ int mjx_compose_batch_device(mjx_ctx *ctx, const mjx_image_desc_t *items_dev, in
     if(d->device != ctx->device) return MJX_ERR_ARG;
     if((rv = ensure_scratch(ctx, k2_scratch_bytes())) != MJX_OK) return rv;
     int         launches = 0;
-    cudaError_t e = launch_k2(ctx->stream, items_dev, n, d->view, block_x, block_y, ctx->scratch, ctx->strict, ctx->sm_count, ctx->class_mask, &launches);
+    const K2Side side = {ctx->side_stream, ctx->side_fork, ctx->side_join};
+    cudaError_t  e = launch_k2(ctx->stream, items_dev, n, d->view, block_x, block_y, ctx->scratch, ctx->strict, ctx->sm_count, ctx->class_mask, &launches,
+                               ctx->overlap ? &side : nullptr);
     ctx->launches += launches;
     if(e != cudaSuccess) return fail(ctx, e, "k2_compose_kernel");
     return MJX_OK;
@@ -691,8 +713,9 @@ int mjx_compose_batch_host(mjx_ctx *ctx, const mjx_host_image_t *items, int n, c
                 }
             MJX_CUDA(ctx, cudaMemcpyAsync(ctx->desc_dev, desc, dbytes, cudaMemcpyHostToDevice, ctx->stream));
             int         launches = 0;
-            cudaError_t e = launch_k2(ctx->stream, (const mjx_image_desc_t *)ctx->desc_dev, n, d->view, block_x, block_y, ctx->scratch,
-                                      ctx->strict, ctx->sm_count, ctx->class_mask, &launches);
+            const K2Side side = {ctx->side_stream, ctx->side_fork, ctx->side_join};
+            cudaError_t  e = launch_k2(ctx->stream, (const mjx_image_desc_t *)ctx->desc_dev, n, d->view, block_x, block_y, ctx->scratch,
+                                       ctx->strict, ctx->sm_count, ctx->class_mask, &launches, ctx->overlap ? &side : nullptr);
             ctx->launches += launches;
             if(e != cudaSuccess) return fail(ctx, e, "k2_compose_kernel");
             MJX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -91,6 +91,12 @@ struct mjx_ctx {
     // extra streams for the pipelined batch-host path
     static const int kPipe = 3;
     cudaStream_t pipe[kPipe] = {};
+
+    // K2 runs its two kernels side by side: the OPAQUE/U kernel on this low-priority stream, forked from and joined
+    // back into `stream` with the two events (k2_compose.cu: launch_k2)
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t  side_fork = nullptr, side_join = nullptr;
+    int          overlap = 1;
 };
 
 namespace mjx {
@@ -112,8 +118,14 @@ cudaError_t launch_classify(cudaStream_t s, mjx_dropon *d);
 cudaError_t launch_count_classes(cudaStream_t s, const mjx_dropon *d, unsigned long long *counts_dev);
 // after classification: fill the work lists and the compact generic-class arrays (slab2 allocated)
 cudaError_t launch_build_lists(cudaStream_t s, mjx_dropon *d, uint32_t *chunk_counts_dev, int *launches);
+// side (optional): stream + fork/join events for running the OPAQUE/U kernel beside the G kernel
+struct K2Side {
+    cudaStream_t stream;
+    cudaEvent_t  fork, join;
+};
 cudaError_t launch_k2(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, const DropView &view, int block_x,
-                      int block_y, void *scratch, int strict, int sm_count, int class_mask, int *launches);
+                      int block_y, void *scratch, int strict, int sm_count, int class_mask, int *launches,
+                      const K2Side *side = nullptr);
 // dc_compact (optional, n == 1): per component a device array [hreal][wreal] the rewrite kernel takes the DCs from
 cudaError_t launch_k3(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, int ncomp, const mjx_effect_op_t *ops,
                       int nops, int *launches, const int16_t *const *dc_compact = nullptr);

@@ -202,6 +202,20 @@ def test_k2_device_batch_mixed_quant_tables(engine, port):
         nG += a
         nbad += b
     print(f"\nK2 mixed quant tables: {len(quals)} images, {nG} generic coefficients, {nbad} differ by one step")
+    # the batch is large enough for the two K2 kernels to run side by side (the default); one after the other must
+    # give the same bytes
+    side_by_side = [batch.download_image(i) for i in range(len(dec))]
+    for i, d in enumerate(dec):
+        batch.upload_image(i, d[3])
+    engine.set_overlap(False)
+    try:
+        engine.compose_batch_device(batch.descs_dev, batch.n, cd, g["block_x"], g["block_y"])
+        engine.sync()
+    finally:
+        engine.set_overlap(True)
+    for i in range(len(dec)):
+        for a, b in zip(side_by_side[i], batch.download_image(i)):
+            assert np.array_equal(a, b), ("overlap on/off", i)
     cd.free()
     batch.free()
 
