@@ -189,13 +189,16 @@ __global__ void __launch_bounds__(THREADS) k2_simple_kernel(const FastParams p) 
     for(int k = threadIdx.x; k < ni * 8; k += THREADS) {
         const uint4    w = __ldg(reinterpret_cast<const uint4 *>(&p.items[i0 + (k >> 3)].q[c][(k & 7) * 8]));
         const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-        float         *dq = &s_q[k >> 3][(k & 7) * 8], *drq = &s_rq[k >> 3][(k & 7) * 8];
+        // row r of a table lives as two float4: entries 0..3 at [r * 4], entries 4..7 at [32 + r * 4], so that the 8
+        // lanes of a block read 128 contiguous bytes per access (rows side by side at stride 32 B were a 2-way conflict)
+        float *dq = &s_q[k >> 3][(k & 7) * 4], *drq = &s_rq[k >> 3][(k & 7) * 4];
+        float  q[8];
 #pragma unroll
-        for(int j = 0; j < 4; j++) {
-            const float q0 = fmaxf((float)(ww[j] & 0xffffu), 1.0f), q1 = fmaxf((float)(ww[j] >> 16), 1.0f);
-            *reinterpret_cast<float2 *>(dq + 2 * j) = make_float2(q0, q1);
-            *reinterpret_cast<float2 *>(drq + 2 * j) = make_float2(quant_rcp_fast(q0), quant_rcp_fast(q1));
-        }
+        for(int j = 0; j < 4; j++) q[2 * j] = fmaxf((float)(ww[j] & 0xffffu), 1.0f), q[2 * j + 1] = fmaxf((float)(ww[j] >> 16), 1.0f);
+        *reinterpret_cast<float4 *>(dq) = make_float4(q[0], q[1], q[2], q[3]);
+        *reinterpret_cast<float4 *>(dq + 32) = make_float4(q[4], q[5], q[6], q[7]);
+        *reinterpret_cast<float4 *>(drq) = make_float4(quant_rcp_fast(q[0]), quant_rcp_fast(q[1]), quant_rcp_fast(q[2]), quant_rcp_fast(q[3]));
+        *reinterpret_cast<float4 *>(drq + 32) = make_float4(quant_rcp_fast(q[4]), quant_rcp_fast(q[5]), quant_rcp_fast(q[6]), quant_rcp_fast(q[7]));
     }
 
     const uint32_t  e = __ldg(p.drop.list_simple + tile * 32 + t);
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(THREADS) k2_simple_kernel(const FastParams p) 
         const int                stride = __shfl_sync(0xffffffffu, d_stride, k), rows = __shfl_sync(0xffffffffu, d_rows, k);
         if(!valid || row >= rows || col >= stride) continue;
         int16_t      *ip = reinterpret_cast<int16_t *>(plane) + ((size_t)row * stride + col) * 64 + r * 8;
-        const float4 ra = *reinterpret_cast<const float4 *>(&s_rq[k][r * 8]), rb = *reinterpret_cast<const float4 *>(&s_rq[k][r * 8 + 4]);
+        const float4 ra = *reinterpret_cast<const float4 *>(&s_rq[k][r * 4]), rb = *reinterpret_cast<const float4 *>(&s_rq[k][32 + r * 4]);
         Row8         out;
         if(opaque) { // trunc(D / q), the image block is not read
             out.w[0] = tdiv_pair(D[0], f2(ra.x, ra.y));
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(THREADS) k2_simple_kernel(const FastParams p) 
         }
         else {
             const Row8   in = ld_row_stream(ip);
-            const float4 qa = *reinterpret_cast<const float4 *>(&s_q[k][r * 8]), qb = *reinterpret_cast<const float4 *>(&s_q[k][r * 8 + 4]);
+            const float4 qa = *reinterpret_cast<const float4 *>(&s_q[k][r * 4]), qb = *reinterpret_cast<const float4 *>(&s_q[k][32 + r * 4]);
             out.w[0] = uniform_pair(f2((float)row_get(in, 0), (float)row_get(in, 1)), D[0], f2(qa.x, qa.y), f2(ra.x, ra.y), w4);
             out.w[1] = uniform_pair(f2((float)row_get(in, 2), (float)row_get(in, 3)), D[1], f2(qa.z, qa.w), f2(ra.z, ra.w), w4);
             out.w[2] = uniform_pair(f2((float)row_get(in, 4), (float)row_get(in, 5)), D[2], f2(qb.x, qb.y), f2(rb.x, rb.y), w4);
