@@ -54,16 +54,25 @@ __global__ void __launch_bounds__(kThreads) k3_rewrite_kernel(const K3Params p, 
     int16_t  *plane = reinterpret_cast<int16_t *>(im.plane[c]);
     for(int l = blockIdx.x; l < hreal; l += gridDim.x) {
         int16_t *rowp = plane + (size_t)l * stride * 64;
-        for(int k = threadIdx.x >> 3; k < wreal; k += kThreads / 8) {
-            int16_t *bp = rowp + (size_t)k * 64;
-            Row8     row;
-            row.w[0] = row.w[1] = row.w[2] = row.w[3] = 0;
-            if(r == 0) {
-                int dc = first_is_zero ? 0 : (p.dc_compact ? (int)p.dc_compact[(size_t)l * wreal + k] : (int)bp[0]);
-                dc = fold_dc(p, dc, q0);
-                row.w[0] = (uint32_t)dc & 0xffffu;
+        // four blocks per thread and trip: the DC loads of all four are in flight before the first store
+        for(int k0 = threadIdx.x >> 3; k0 < wreal; k0 += 4 * (kThreads / 8)) {
+            int dc[4] = {0, 0, 0, 0};
+            if(r == 0 && !first_is_zero) {
+#pragma unroll
+                for(int u = 0; u < 4; u++) {
+                    const int k = k0 + u * (kThreads / 8);
+                    if(k < wreal) dc[u] = p.dc_compact ? (int)p.dc_compact[(size_t)l * wreal + k] : (int)rowp[(size_t)k * 64];
+                }
             }
-            st_row_stream(bp + r * 8, row);
+#pragma unroll
+            for(int u = 0; u < 4; u++) {
+                const int k = k0 + u * (kThreads / 8);
+                if(k >= wreal) break;
+                Row8 row;
+                row.w[0] = row.w[1] = row.w[2] = row.w[3] = 0;
+                if(r == 0) row.w[0] = (uint32_t)fold_dc(p, dc[u], q0) & 0xffffu;
+                st_row_stream(rowp + (size_t)k * 64 + r * 8, row);
+            }
         }
     }
 }
