@@ -443,6 +443,24 @@ def test_api_compose_vs_reference_live(engine, ref):
     print("\nAPI vs live reference:", stats)
 
 
+def test_api_random_sweep_vs_reference_live(engine, ref):
+    """80 random compose + effect cases through the drop-in API against the reference library run here
+    (profiles/fuzz_parity.py): same return codes, uniform-alpha cases and effects bit-identical, float-blended
+    coefficients within one step at a bounded rate"""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "fuzz_parity.py"), "80", "7"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    t = json.loads(out.stdout)["totals"]
+    print("\nrandom sweep:", t)
+    assert t["cases"] == 80 and t["composes_visible"] > 20
+    assert t["return_code_mismatch"] == 0 and t["max_abs_diff"] <= 1
+    assert t["exact_class_differing"] == 0 and t["effect_differing"] == 0
+    assert t["coefficients_differing"] <= G_RATE * t["coefficients_changed"] + 2
+
+
 def test_api_effects_golden_and_oracle(engine, port):
     import libmodjpeg_b200 as M
 
