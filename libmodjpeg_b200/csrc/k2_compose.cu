@@ -173,7 +173,7 @@ static constexpr int kSimpleImages = 16; // images walked by one CTA of the simp
 // beside the three resident CTAs of the G kernel on every SM (10 240 registers are left there), which is how the two
 // kernels run concurrently (launch_k2).
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k2_simple_kernel(const FastParams p) {
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k2_simple_kernel(const FastParams p) {
     __shared__ __align__(16) float s_q[kSimpleImages][64], s_rq[kSimpleImages][64];
     constexpr int kPerTile = kThreads / THREADS; // CTAs per tile
     const int     r = threadIdx.x & 7, t = (threadIdx.x >> 3) + (blockIdx.x % kPerTile) * (THREADS / 8);
@@ -184,21 +184,40 @@ __global__ void __launch_bounds__(THREADS) k2_simple_kernel(const FastParams p) 
         if(i < p.drop.ncomp && tile >= p.drop.stile_start[i]) c = i;
     const int i0 = blockIdx.y * kSimpleImages, ni = min(p.n - i0, kSimpleImages);
 
-    // float tables of the chunk's images for this component: one 128-bit load = 8 entries per thread, so that the
-    // CTA's start-up is one memory latency (it is exposed when a single small CTA runs beside the G kernel)
-    for(int k = threadIdx.x; k < ni * 8; k += THREADS) {
-        const uint4    w = __ldg(reinterpret_cast<const uint4 *>(&p.items[i0 + (k >> 3)].q[c][(k & 7) * 8]));
-        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-        // row r of a table lives as two float4: entries 0..3 at [r * 4], entries 4..7 at [32 + r * 4], so that the 8
-        // lanes of a block read 128 contiguous bytes per access (rows side by side at stride 32 B were a 2-way conflict)
-        float *dq = &s_q[k >> 3][(k & 7) * 4], *drq = &s_rq[k >> 3][(k & 7) * 4];
-        float  q[8];
+    // float tables of the chunk's images for this component: one 128-bit load = 8 entries per thread (THREADS >= 8 per
+    // image), so that the CTA's start-up is one memory latency (it is exposed when a single small CTA runs beside the G
+    // kernel).  The same threads note which images carry the SAME table as their predecessor in the chunk -- batches
+    // from one encoder setting do throughout -- because trunc(D / q) of an opaque block is then the same row again.
+    __shared__ unsigned s_same[4]; // per table-converting warp: bit g = image g's table equals image g - 1's
+    {
+        const int k = threadIdx.x;
+        bool      eq = false;
+        if(k < ni * 8) {
+            const uint4 w = __ldg(reinterpret_cast<const uint4 *>(&p.items[i0 + (k >> 3)].q[c][(k & 7) * 8]));
+            if(k >= 8) {
+                const uint4 wp = __ldg(reinterpret_cast<const uint4 *>(&p.items[i0 + (k >> 3) - 1].q[c][(k & 7) * 8]));
+                eq = w.x == wp.x && w.y == wp.y && w.z == wp.z && w.w == wp.w;
+            }
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+            // row r of a table lives as two float4: entries 0..3 at [r * 4], entries 4..7 at [32 + r * 4], so that the 8
+            // lanes of a block read 128 contiguous bytes per access (rows side by side at stride 32 B were a 2-way conflict)
+            float *dq = &s_q[k >> 3][(k & 7) * 4], *drq = &s_rq[k >> 3][(k & 7) * 4];
+            float  q[8];
 #pragma unroll
-        for(int j = 0; j < 4; j++) q[2 * j] = fmaxf((float)(ww[j] & 0xffffu), 1.0f), q[2 * j + 1] = fmaxf((float)(ww[j] >> 16), 1.0f);
-        *reinterpret_cast<float4 *>(dq) = make_float4(q[0], q[1], q[2], q[3]);
-        *reinterpret_cast<float4 *>(dq + 32) = make_float4(q[4], q[5], q[6], q[7]);
-        *reinterpret_cast<float4 *>(drq) = make_float4(quant_rcp_fast(q[0]), quant_rcp_fast(q[1]), quant_rcp_fast(q[2]), quant_rcp_fast(q[3]));
-        *reinterpret_cast<float4 *>(drq + 32) = make_float4(quant_rcp_fast(q[4]), quant_rcp_fast(q[5]), quant_rcp_fast(q[6]), quant_rcp_fast(q[7]));
+            for(int j = 0; j < 4; j++) q[2 * j] = fmaxf((float)(ww[j] & 0xffffu), 1.0f), q[2 * j + 1] = fmaxf((float)(ww[j] >> 16), 1.0f);
+            *reinterpret_cast<float4 *>(dq) = make_float4(q[0], q[1], q[2], q[3]);
+            *reinterpret_cast<float4 *>(dq + 32) = make_float4(q[4], q[5], q[6], q[7]);
+            *reinterpret_cast<float4 *>(drq) = make_float4(quant_rcp_fast(q[0]), quant_rcp_fast(q[1]), quant_rcp_fast(q[2]), quant_rcp_fast(q[3]));
+            *reinterpret_cast<float4 *>(drq + 32) = make_float4(quant_rcp_fast(q[4]), quant_rcp_fast(q[5]), quant_rcp_fast(q[6]), quant_rcp_fast(q[7]));
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, eq); // 8 lanes per image, 4 images per warp
+        if((threadIdx.x & 31) == 0 && threadIdx.x < 128) {
+            unsigned m = 0;
+#pragma unroll
+            for(int g = 0; g < 4; g++)
+                if(((b >> (8 * g)) & 0xffu) == 0xffu) m |= 1u << ((threadIdx.x >> 5) * 4 + g);
+            s_same[threadIdx.x >> 5] = m;
+        }
     }
 
     const uint32_t  e = __ldg(p.drop.list_simple + tile * 32 + t);
@@ -228,21 +247,37 @@ __global__ void __launch_bounds__(THREADS) k2_simple_kernel(const FastParams p) 
         d_rows = im.rows[c];
     }
     __syncthreads();
+    const unsigned same = s_same[0] | s_same[1] | s_same[2] | s_same[3];
+    // likewise for the plane geometry: images of one size share the block's byte offset, only the plane base changes
+    const int      p_stride = __shfl_up_sync(0xffffffffu, d_stride, 1), p_rows = __shfl_up_sync(0xffffffffu, d_rows, 1);
+    const unsigned gsame = __ballot_sync(0xffffffffu, lane > 0 && lane < ni && p_stride == d_stride && p_rows == d_rows);
 
+    Row8   out = {{0u, 0u, 0u, 0u}};
+    bool   have = false; // `out` is trunc(D / q) for the table of the image before this one
+    bool   on = false;   // the block lies on the image (for the current geometry)
+    size_t off = 0;      // byte offset of the lane's row in the plane (for the current geometry)
     for(int k = 0; k < ni; k++) {
         const unsigned long long plane = __shfl_sync(0xffffffffu, d_plane, k);
-        const int                stride = __shfl_sync(0xffffffffu, d_stride, k), rows = __shfl_sync(0xffffffffu, d_rows, k);
-        if(!valid || row >= rows || col >= stride) continue;
-        int16_t      *ip = reinterpret_cast<int16_t *>(plane) + ((size_t)row * stride + col) * 64 + r * 8;
-        const float4 ra = *reinterpret_cast<const float4 *>(&s_rq[k][r * 4]), rb = *reinterpret_cast<const float4 *>(&s_rq[k][32 + r * 4]);
-        Row8         out;
-        if(opaque) { // trunc(D / q), the image block is not read
-            out.w[0] = tdiv_pair(D[0], f2(ra.x, ra.y));
-            out.w[1] = tdiv_pair(D[1], f2(ra.z, ra.w));
-            out.w[2] = tdiv_pair(D[2], f2(rb.x, rb.y));
-            out.w[3] = tdiv_pair(D[3], f2(rb.z, rb.w));
+        if(!((gsame >> k) & 1u)) { // warp-uniform
+            const int stride = __shfl_sync(0xffffffffu, d_stride, k), rows = __shfl_sync(0xffffffffu, d_rows, k);
+            on = valid && row < rows && col < stride;
+            off = (((size_t)row * stride + col) * 64 + r * 8) * sizeof(int16_t);
+        }
+        have = have && ((same >> k) & 1u);
+        if(!on) continue;
+        int16_t *ip = reinterpret_cast<int16_t *>(plane + off);
+        if(opaque) { // trunc(D / q), the image block is not read; same table as before: same row again
+            if(!have) {
+                const float4 ra = *reinterpret_cast<const float4 *>(&s_rq[k][r * 4]), rb = *reinterpret_cast<const float4 *>(&s_rq[k][32 + r * 4]);
+                out.w[0] = tdiv_pair(D[0], f2(ra.x, ra.y));
+                out.w[1] = tdiv_pair(D[1], f2(ra.z, ra.w));
+                out.w[2] = tdiv_pair(D[2], f2(rb.x, rb.y));
+                out.w[3] = tdiv_pair(D[3], f2(rb.z, rb.w));
+                have = true;
+            }
         }
         else {
+            const float4 ra = *reinterpret_cast<const float4 *>(&s_rq[k][r * 4]), rb = *reinterpret_cast<const float4 *>(&s_rq[k][32 + r * 4]);
             const Row8   in = ld_row_stream(ip);
             const float4 qa = *reinterpret_cast<const float4 *>(&s_q[k][r * 4]), qb = *reinterpret_cast<const float4 *>(&s_q[k][32 + r * 4]);
             out.w[0] = uniform_pair(f2((float)row_get(in, 0), (float)row_get(in, 1)), D[0], f2(qa.x, qa.y), f2(ra.x, ra.y), w4);
