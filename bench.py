@@ -400,6 +400,14 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
     ms_generic = time_masked(2) if counts["G"] else 0.0
     # clocks / throttle reasons sampled from just before the timed steps to the end of the per-kernel timings
     # (the same kernels back to back: the GPU is under the bench's load for the whole window)
+    if rank == 0:
+        # nvidia-smi needs a few hundred ms before its first line on some boxes: keep the same kernels running (untimed)
+        # until a handful of samples exist, so that the clocks reported are always clocks under this load
+        t_wait = time.time()
+        while sum(1 for t, _ in sampler.lines if t >= t0 - 0.05) < 5 and time.time() - t_wait < 4.0 and sampler.proc is not None:
+            for _ in range(10):
+                step()
+            torch.cuda.synchronize(dev)
     clocks = sampler.stop(t0, time.time()) if rank == 0 else None
 
     # ---- the other two kernels of the path, on the same resident batch (rank 0 reports) -----------
