@@ -10,11 +10,13 @@
 //           the closed form of the reference's 64 sparse DCT-domain products, within +-1
 //           quantisation step of it.
 //
-// Two kernels per call (one launch each, any number of images):
+// Two kernels per call (one launch each, any number of images; side by side for batches of >= 64
+// images, see launch_k2):
 //   k2_simple_kernel   OPAQUE/U list; 8 lanes per block (lane r = row r, one 128-bit access per
 //                      plane), D row kept in registers while the lanes walk 16 images whose quant
-//                      tables were converted once per CTA into shared memory; built for memory
-//                      parallelism (3.6 TB/s write-only)
+//                      tables were converted once per CTA into shared memory; no global load in the
+//                      image loop, opaque rows reused across images with identical tables; bound by
+//                      its writes (6 TB/s write-only)
 //   k2_generic_kernel  G list; one thread owns one block (all 64 coefficients in registers as 32
 //                      fp32 pairs, so the 2-D transforms need no shuffles), arithmetic on packed
 //                      fp32 (FADD2 / FMUL2 / FFMA2).  A CTA of 4 warps shares a tile of 32 list
@@ -155,7 +157,8 @@ __global__ void __launch_bounds__(kThreads) k2_strict_kernel(const StrictParams 
 // 32 list entries (one component, the list is padded per component) and walks a chunk of kSimpleImages
 // images with the lane's D row in registers.  The chunk's quantisation tables are converted once per CTA
 // into shared memory (q and the biased reciprocal as floats), so the per-image path is
-// 2-4 broadcast LDS.128 + 4 packed-fp32 pair operations + one coalesced 128-bit store.
+// 2-4 conflict-free LDS.128 + 4 packed-fp32 pair operations + one coalesced 128-bit store -- and for an
+// opaque block whose image has the same table and geometry as the one before, just the store.
 // Arithmetic: tdiv_pair / uniform_pair (mjx_math.cuh), bit-exact with the reference.
 
 struct FastParams {
