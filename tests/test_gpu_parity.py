@@ -173,7 +173,9 @@ def test_k2_device_batch_mixed_quant_tables(engine, port):
     from libmodjpeg_b200.batch import DeviceBatch
 
     W_, H_ = 208, 144
-    quals = [35 + 2 * i for i in range(32)] * 4 + [50, 75]  # 130 images > 96 per item: two chunks per tile
+    # 130 images > 96 per item: two chunks per tile.  Runs of one, two and three images with the SAME table next to
+    # images with different ones: the OPAQUE/U kernel reuses an opaque row only while the table stays the same
+    quals = [35 + 2 * i for i in range(32)] * 2 + [35 + 2 * (i // 3) for i in range(48)] + [50, 50, 75, 75, 75, 50] * 3
     base = {q: _decode(util.jpeg_bytes(W_, H_, "420", q, seed=500 + q)) for q in sorted(set(quals))}
     dec = [base[q] for q in quals]
     info, samp = dec[0][1], dec[0][2]
