@@ -222,6 +222,82 @@ def test_k2_device_batch_mixed_quant_tables(engine, port):
     batch.free()
 
 
+@pytest.mark.parametrize("n_images", [20, 76])
+def test_k2_device_batch_mixed_geometry_and_tables(engine, port, n_images):
+    """one launch over images of TWO plane geometries (the smaller image ends inside the dropon, so part of the
+    dropon's blocks do not lie on it) and two quantisation tables, interleaved in runs: the kernels skip absent
+    blocks per image and may reuse offsets / opaque rows only while geometry / table stay the same.
+    20 images take the one-after-the-other launch, 76 the side-by-side one."""
+    from libmodjpeg_b200 import Layout, capi
+    from libmodjpeg_b200.batch import DeviceBatch
+
+    big = {q: _decode(util.jpeg_bytes(320, 240, "420", q, seed=900 + q)) for q in (60, 90)}
+    small = {q: _decode(util.jpeg_bytes(208, 144, "420", q, seed=950 + q)) for q in (60, 90)}
+    info, samp = big[60][1], big[60][2]
+    shapes_big = [p.shape[:2] for p in big[60][3]]
+    shapes_small = [p.shape[:2] for p in small[60][3]]
+    raw = util.logo_rgba(288, 208, 64, 27)  # reaches beyond the small image on both axes
+    i3, a3, scs, sblend = util.ingest_raw(raw, 2, 255)
+
+    def expect(planes, qt, shapes):
+        """oracle on the planes zero-padded to the big geometry (blocks are independent), cropped back"""
+        pad = [np.zeros((sb[0], sb[1], 64), np.int16) for sb in shapes_big]
+        for a, b in zip(pad, planes):
+            a[:b.shape[0], :b.shape[1]] = b
+        rv, g, D, Wc = util.oracle_compose(port, pad, qt, info["width"], info["height"], info["colorspace"], samp, i3, a3, scs, sblend, 5, 0, 0)
+        assert rv == 0 and g["visible"]
+        return [a[:r, :w_].copy() for a, (r, w_) in zip(pad, shapes)], g
+
+    want_big = {q: expect([p.copy() for p in big[q][3]], big[q][4], shapes_big) for q in (60, 90)}
+    want_small = {q: expect([p.copy() for p in small[q][3]], small[q][4], shapes_small) for q in (60, 90)}
+    g = want_big[60][1]
+    # pattern of (geometry, table) in runs of one to three
+    pat = [("b", 60), ("b", 60), ("s", 60), ("s", 90), ("s", 90), ("b", 90), ("s", 60), ("b", 60), ("b", 90), ("b", 90), ("b", 90), ("s", 90)]
+    seq = [pat[i % len(pat)] for i in range(n_images)]
+    nb, ns = sum(1 for k, _ in seq if k == "b"), sum(1 for k, _ in seq if k == "s")
+    bb, bs = DeviceBatch(engine, shapes_big, nb), DeviceBatch(engine, shapes_small, ns)
+    ptr_rows, ib, is_ = [], 0, 0
+    where = []
+    for kind, q in seq:
+        if kind == "b":
+            bb.upload_image(ib, big[q][3])
+            d = capi.make_image_descs([[bb.plane_ptr(ib, c) for c in range(3)]], [s_ for _, s_ in shapes_big], [r for r, _ in shapes_big], np.stack(big[q][4]))
+            where.append((bb, ib))
+            ib += 1
+        else:
+            bs.upload_image(is_, small[q][3])
+            d = capi.make_image_descs([[bs.plane_ptr(is_, c) for c in range(3)]], [s_ for _, s_ in shapes_small], [r for r, _ in shapes_small], np.stack(small[q][4]))
+            where.append((bs, is_))
+            is_ += 1
+        ptr_rows.append(d)
+    descs = np.concatenate(ptr_rows)
+    descs_dev = engine.device_alloc(descs.nbytes)
+    engine.copy_h2d(descs_dev, descs.view(np.uint8).reshape(-1))
+    engine.sync()
+    cd = engine.dropon_compile(i3, a3, scs, Layout.make(info["colorspace"], samp), (g["blockoffset_x"], g["blockoffset_y"]),
+                               (g["crop_x"], g["crop_y"], g["crop_w"], g["crop_h"]))
+    cls_maps = [cd.download(c)[2] for c in range(3)]
+    engine.compose_batch_device(descs_dev, n_images, cd, g["block_x"], g["block_y"])
+    engine.sync()
+    nG = nbad = 0
+    for i, (kind, q) in enumerate(seq):
+        batch, idx = where[i]
+        got = batch.download_image(idx)
+        if kind == "b":
+            a, b = _check_planes(got, want_big[q][0], big[q][3], cls_maps, (g["block_x"], g["block_y"]), samp, ("mixed geometry", i, kind, q))
+        else:
+            # the class maps reach beyond the small planes: crop them to the plane for the masks
+            maps = [m[:got[c].shape[0] - g["block_y"] * samp[c][1], :got[c].shape[1] - g["block_x"] * samp[c][0]] for c, m in enumerate(cls_maps)]
+            a, b = _check_planes(got, want_small[q][0], small[q][3], maps, (g["block_x"], g["block_y"]), samp, ("mixed geometry", i, kind, q))
+        nG += a
+        nbad += b
+    print(f"\nK2 mixed geometry ({n_images} images): {nG} generic coefficients, {nbad} differ by one step")
+    engine.device_free(descs_dev)
+    cd.free()
+    bb.free()
+    bs.free()
+
+
 def test_k2_with_oracle_compiled_dropon(engine, port):
     """K2 in isolation: the dropon coefficients come from the oracle (mjx_dropon_from_coefficients)"""
     from libmodjpeg_b200 import Layout
