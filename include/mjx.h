@@ -106,6 +106,12 @@ int         mjx_ctx_use_own_stream(mjx_ctx *ctx);                /* back to the 
 /* strict = 1: K2 runs as one kernel that reproduces the reference's int16 wrap-around on out-of-range
  * products (adversarial streams); default 0: the fast kernels, identical on every encoder-produced JPEG */
 int         mjx_ctx_set_strict(mjx_ctx *ctx, int strict);
+/* class G blocks (non-uniform alpha) of batches: the inverse transform runs on the tensor cores (tcgen05, fp16 operands,
+ * fp32 accumulation; libmodjpeg_b200/csrc/k2_generic_tc.cu).  Its integer operand trick needs every coefficient in the
+ * baseline range [-1024, 1023] (DC 11 bits, AC 10 bits: what ITU-T T.81 allows an 8-bit JPEG to carry).
+ * mode 1 (default): the kernel checks that per block and hands blocks outside the range to the fp32 kernel;
+ * mode 2: no check, the caller vouches for the range; mode 0: fp32 kernel only.  Env MJX_K2_TC sets the initial mode. */
+int         mjx_ctx_set_tensor_core(mjx_ctx *ctx, int mode);
 /* on = 1 (default): mjx_compose_batch_host runs K2 directly on page-locked (GPU-addressable) host planes, so only
  * the blocks the dropon touches cross PCIe; 0: always stage the region under the dropon through device memory */
 int         mjx_ctx_set_zero_copy(mjx_ctx *ctx, int on);

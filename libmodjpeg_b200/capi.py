@@ -97,6 +97,7 @@ def load_mjx() -> C.CDLL:
     L.mjx_ctx_set_stream.argtypes = [vp, vp]
     L.mjx_ctx_use_own_stream.argtypes = [vp]
     L.mjx_ctx_set_strict.argtypes = [vp, C.c_int]
+    L.mjx_ctx_set_tensor_core.argtypes = [vp, C.c_int]
     L.mjx_ctx_stream.argtypes = [vp]
     L.mjx_ctx_stream.restype = vp
     L.mjx_ctx_sync.argtypes = [vp]
@@ -257,6 +258,10 @@ class Engine:
     def set_overlap(self, on: bool) -> None:
         """large batches: OPAQUE/U kernel beside the G kernel (default) or one after the other"""
         self._check(self.lib.mjx_ctx_set_overlap(self.ctx, 1 if on else 0), "mjx_ctx_set_overlap")
+
+    def set_tensor_core(self, mode: int) -> None:
+        """G class of batches: 1 tensor-core kernel with coefficient range check (default), 2 without check, 0 fp32 kernel"""
+        self._check(self.lib.mjx_ctx_set_tensor_core(self.ctx, mode), "mjx_ctx_set_tensor_core")
 
     def set_strict(self, strict: bool) -> None:
         """strict: one K2 kernel with the reference's int16 wrap-around (adversarial inputs); default fast kernels"""

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kChunk) list_fill_kernel(const ListParams p, c
 }
 
 // compact float arrays of the generic blocks; 8 lanes per block, lane r = row r
-__global__ void __launch_bounds__(256) generic_prepare_kernel(const DropView dv, float *gDs, float *gA) {
+__global__ void __launch_bounds__(256) generic_prepare_kernel(const DropView dv, float *gDs, float *gA, float *gAd) {
     const int r = threadIdx.x & 7;
     const int g = blockIdx.x * 32 + (threadIdx.x >> 3);
     if(g >= dv.n_generic) return;
@@ -106,24 +106,33 @@ __global__ void __launch_bounds__(256) generic_prepare_kernel(const DropView dv,
     const float    isc[8] = MJX_INV_SCALE_INIT;
     const float    pr = c_inv_scale[r];
     const unsigned mask = group_mask();
-    float          ds[8], a[8];
+    float          ds[8], a[8], dp[8];
 #pragma unroll
     for(int i = 0; i < 8; i++) {
         const float s = pr * isc[i];
         ds[i] = (float)D[i] * s;
+        dp[i] = ds[i];
         a[i] = (float)W[i] * (s * (1.0f / 255.0f));
     }
     idct8(a);               // lane = vertical frequency, elements = pixel column
     transpose8(a, r, mask); // lane = pixel column, elements = vertical frequency
     idct8(a);               // elements = pixel row
     transpose8(a, r, mask); // lane = pixel row: natural [py][px]
+    idct8(dp);              // the overlay's pixels (level-shifted), the same way: what the tensor-core G kernel blends against
+    transpose8(dp, r, mask);
+    idct8(dp);
+    transpose8(dp, r, mask);
     float4 *o = reinterpret_cast<float4 *>(gDs + (size_t)g * 64 + r * 8);
     o[0] = make_float4(ds[0], ds[1], ds[2], ds[3]);
     o[1] = make_float4(ds[4], ds[5], ds[6], ds[7]);
     // A is stored "Q-paired" for k2_generic_kernel: float (8*i + k) * 2 + h  =  A[row 2i + h][col k]
     float *ao = gA + (size_t)g * 64 + (size_t)(r >> 1) * 16 + (r & 1);
+    float *po = gAd + (size_t)g * 64 + (size_t)(r >> 1) * 16 + (r & 1);
 #pragma unroll
-    for(int k = 0; k < 8; k++) ao[2 * k] = a[k];
+    for(int k = 0; k < 8; k++) {
+        ao[2 * k] = a[k];
+        po[2 * k] = a[k] * dp[k];
+    }
 }
 
 cudaError_t launch_build_lists(cudaStream_t s, mjx_dropon *d, uint32_t *chunk_counts_dev, int *launches) {
@@ -151,7 +160,7 @@ cudaError_t launch_build_lists(cudaStream_t s, mjx_dropon *d, uint32_t *chunk_co
     if(launches) *launches += 3;
     if(d->view.n_generic > 0) {
         generic_prepare_kernel<<<(d->view.n_generic + 31) / 32, 256, 0, s>>>(d->view, const_cast<float *>(d->view.gDs),
-                                                                              const_cast<float *>(d->view.gA));
+                                                                              const_cast<float *>(d->view.gA), const_cast<float *>(d->view.gAd));
         if((e = cudaGetLastError()) != cudaSuccess) return e;
         if(launches) *launches += 1;
     }

@@ -37,7 +37,7 @@
 //
 // Roofline: HBM.  Algorithmic bytes per block: T 0, OPAQUE 128 (write), U/G 256 (read + write),
 // plus the compiled dropon once per launch (L2 / shared-memory resident across the images).
-#include "mjx_device.cuh"
+#include "k2_common.cuh"
 
 namespace mjx {
 
@@ -160,15 +160,6 @@ __global__ void __launch_bounds__(kThreads) k2_strict_kernel(const StrictParams 
 // 2-4 conflict-free LDS.128 + 4 packed-fp32 pair operations + one coalesced 128-bit store -- and for an
 // opaque block whose image has the same table and geometry as the one before, just the store.
 // Arithmetic: tdiv_pair / uniform_pair (mjx_math.cuh), bit-exact with the reference.
-
-struct FastParams {
-    DropView                drop;
-    const mjx_image_desc_t *items;
-    unsigned int           *counter; // work-stealing counter of the generic kernel
-    int                     n;       // images
-    int                     block_x, block_y;
-    int                     images_per_item;
-};
 
 static constexpr int kSimpleImages = 16; // images walked by one CTA of the simple kernel
 
@@ -314,60 +305,13 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k2_simple_kernel(cons
 // scalar adds per pass instead of a register transpose.  ~1.5 k issue slots per block (the
 // scalar fp32 version needed ~2.3 k); measured balance and what limits it: DESIGN.md 4.2.
 
-static constexpr int kGStages = 2;
-// Shared-memory blocks are PADDED by one 16-byte chunk (stride 144 B for int16 blocks, 272 B for
-// float blocks): lane t reading chunk c of "its" block t hits bank group (t + c) mod 8, so the
-// thread-per-block 128-bit accesses are conflict-free AND every address is lane base + immediate
-// (an XOR swizzle costs a LOP3 + IADD per access: ~100 issue slots per block).
-static constexpr int kInStride = 144, kF32Stride = 272;
-static constexpr int kInBytes = 32 * kInStride; // one image's 32 blocks
-static constexpr int kQRawBytes = 128;          // its quantisation table as stored (64 x uint16)
-static constexpr int kAddrBytes = 32 * 8;       // global addresses of the 32 blocks
-static constexpr int kStageBytes = kInBytes + kQRawBytes + kAddrBytes;
-static constexpr int kTabBytes = 3 * 64 * 4; // q * prescale, q, biased 1/q as floats (current image)
-static constexpr int kWarpBytes = kGStages * kStageBytes + kTabBytes;
-static constexpr int kTileHalf = 32 * kF32Stride; // A (Q-paired) or Ds of the tile
-static constexpr int kTileBytes = 2 * kTileHalf;
-static constexpr int g_smem(int warps) { return kTileBytes + warps * kWarpBytes; }
-
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-// 16 bytes global -> shared; nbytes == 0 zero-fills without touching `src` (no branch for absent blocks)
-__device__ __forceinline__ void cp_async16(unsigned dst, const void *src, unsigned nbytes = 16u) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// sign-extend with PRMT, convert with the full-rate I2FP.F32.S32 (the compiler's I2F.S16 issues at 1/4 rate)
-// (PTX prmt replicates the sign of a byte when bit 3 of its selector nibble is set; the
-// __byte_perm() intrinsic masks that bit off, hence the inline asm)
-__device__ __forceinline__ float s16lo(uint32_t w) {
-    int v;
-    asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(v) : "r"(w));
-    return (float)v;
-}
-__device__ __forceinline__ float s16hi(uint32_t w) { return (float)((int32_t)w >> 16); }
-__device__ __forceinline__ F2 s16pair(uint32_t w) { return f2(s16lo(w), s16hi(w)); }
-
-// forward AAN scale of the pair (row r; cols 2j, 2j+1), indexed 4r + j
-struct FwdScale2 {
-    float2 v[32];
-};
-static __constant__ FwdScale2 c_fwd2 = {{
-#define MJX_F(r, a, b) {(float)(r * a), (float)(r * b)}
-#define MJX_FROW(r)                                                                                              \
-    MJX_F(r, 0.35355339059327376, 0.25489778955207959), MJX_F(r, 0.27059805007309851, 0.30067244346752264),     \
-        MJX_F(r, 0.35355339059327376, 0.44998811156820786), MJX_F(r, 0.65328148243818826, 1.28145772387075308)
-    MJX_FROW(0.35355339059327376), MJX_FROW(0.25489778955207959), MJX_FROW(0.27059805007309851), MJX_FROW(0.30067244346752264),
-    MJX_FROW(0.35355339059327376), MJX_FROW(0.44998811156820786), MJX_FROW(0.65328148243818826), MJX_FROW(1.28145772387075308)
-#undef MJX_FROW
-#undef MJX_F
-}};
-
-template <int kGWarps, int kMinCtas>
+// kRedo: second pass behind the tensor-core kernel -- only the (tile, image) pairs whose bit is set in p.redo_bits are
+// processed (blocks with coefficients outside the baseline range, which that kernel left alone); exits at once when
+// the count is zero.
+template <int kGWarps, int kMinCtas, bool kRedo>
 __global__ void __launch_bounds__(kGWarps * 32, kMinCtas) k2_generic_kernel(const FastParams p) {
     constexpr int kGThreads = kGWarps * 32;
+    if(kRedo && *reinterpret_cast<volatile const unsigned int *>(p.redo_count) == 0u) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_item;
     const int      lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -389,7 +333,7 @@ __global__ void __launch_bounds__(kGWarps * 32, kMinCtas) k2_generic_kernel(cons
 
     for(;;) {
         __syncthreads(); // every warp is done with the previous item's tile (and with s_item)
-        if(threadIdx.x == 0) s_item = (int)atomicAdd(p.counter, 1u);
+        if(threadIdx.x == 0) s_item = (int)atomicAdd(p.counter + (kRedo ? 2 : 0), 1u);
         __syncthreads();
         const int item = s_item;
         if(item >= nitems) break;
@@ -442,6 +386,10 @@ __global__ void __launch_bounds__(kGWarps * 32, kMinCtas) k2_generic_kernel(cons
             unsigned long long      *addr = reinterpret_cast<unsigned long long *>(sb + kInBytes + kQRawBytes);
             unsigned long long       a = 0;
             if(my_valid && my_row < rows && my_col < stride) a = plane + ((unsigned long long)my_row * stride + my_col) * 128ull;
+            if(kRedo) {
+                const long long bit = (long long)cur_tile * p.n + (i0 + k * kGWarps);
+                if(!((__ldg(p.redo_bits + (bit >> 5)) >> (bit & 31)) & 1u)) a = 0;
+            }
             addr[lane] = a;
             const bool all_there = __all_sync(0xffffffffu, a != 0); // the usual case: every block of the tile lies on this image
             __syncwarp();
@@ -588,13 +536,21 @@ cudaError_t launch_selftest_reciprocal(cudaStream_t s, unsigned long long *misma
 // launcher
 // =========================================================================================
 
-size_t k2_scratch_bytes() { return 256; }
+static constexpr int kTcMinImages = 24; // below this the 12-warp CTAs of the tensor-core kernel run mostly empty
 
-cudaError_t launch_k2(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, const DropView &view, int block_x,
-                      int block_y, void *scratch, int strict, int sm_count, int class_mask, int *launches, const K2Side *side) {
+static size_t redo_bitmap_bytes(int n, const DropView &view) {
+    const long long bits = (long long)(view.n_generic / 32) * (n > 0 ? n : 0);
+    return (size_t)((bits + 31) / 32 * 4 + 255) / 256 * 256;
+}
+// [0] work counter of the G kernel, [1] redo count, [2] work counter of the redo pass, [64..] redo bitmap
+size_t k2_scratch_bytes(int n, const DropView &view) { return 256 + redo_bitmap_bytes(n, view); }
+
+cudaError_t launch_k2(const K2Launch &L, const mjx_image_desc_t *items_dev, int n, const DropView &view, int block_x, int block_y) {
     if(n <= 0 || view.total_blocks <= 0) return cudaSuccess;
-    cudaError_t e;
-    if(strict) {
+    cudaStream_t s = L.stream;
+    int         *launches = L.launches;
+    cudaError_t  e;
+    if(L.strict) {
         StrictParams p;
         p.drop = view;
         p.block_x = block_x;
@@ -611,31 +567,38 @@ cudaError_t launch_k2(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, 
     }
     if(view.n_simple == 0 && view.n_generic == 0) return cudaSuccess;
 
-    // generic kernel: 4 warps per CTA, 3 CTAs per SM (142 registers, 60 KB shared memory).  8 warps x 2 CTAs at 128
+    // fp32 generic kernel: 4 warps per CTA, 3 CTAs per SM (142 registers, 60 KB shared memory).  8 warps x 2 CTAs at 128
     // registers was measured slower (1.89 vs 1.72 ms): the spills cost more than the extra warps hide.
     constexpr int g_warps = 4;
-    static int    ctas_per_sm = 0; // idempotent; a benign race at worst computes it twice
-    if(ctas_per_sm == 0) {
-        if((e = cudaFuncSetAttribute(k2_generic_kernel<g_warps, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem(g_warps))) != cudaSuccess) return e;
+    K2Dev         local_dev;
+    K2Dev        *dev = L.dev ? L.dev : &local_dev;
+    if(!dev->g_attr) { // function attributes are per device: cached in the ctx, not in a process-wide static
+        if((e = cudaFuncSetAttribute(k2_generic_kernel<g_warps, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem(g_warps))) != cudaSuccess) return e;
+        if((e = cudaFuncSetAttribute(k2_generic_kernel<g_warps, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem(g_warps))) != cudaSuccess) return e;
         int occ = 0;
-        if((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_generic_kernel<g_warps, 3>, g_warps * 32, g_smem(g_warps))) != cudaSuccess) return e;
-        ctas_per_sm = occ > 0 ? occ : 1;
+        if((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k2_generic_kernel<g_warps, 3, false>, g_warps * 32, g_smem(g_warps))) != cudaSuccess) return e;
+        dev->g_ctas_per_sm = occ > 0 ? occ : 1;
+        dev->g_attr = true;
     }
+    const int ctas_per_sm = dev->g_ctas_per_sm;
+    const bool use_tc = L.tc != 0 && n >= kTcMinImages && view.n_generic > 0 && (L.class_mask & 2);
     FastParams p;
     p.drop = view;
     p.items = items_dev;
-    p.counter = reinterpret_cast<unsigned int *>(scratch);
+    p.counter = reinterpret_cast<unsigned int *>(L.scratch);
+    p.redo_count = p.counter + 1;
+    p.redo_bits = p.counter + 64;
     p.n = n;
     p.block_x = block_x;
     p.block_y = block_y;
     p.images_per_item = n < 24 * g_warps ? n : 24 * g_warps; // per warp: <= 32 (one descriptor per lane); 16..32 measured within 1.5 %
 
     // Both classes present and a batch large enough to fill the machine: the two kernels run side by side.  The G kernel
-    // (fp32-pipe bound, ~45 % of HBM) is launched first and keeps its 3 CTAs per SM; the OPAQUE/U kernel (write bound)
-    // follows on the low-priority side stream in its 128-thread shape, one CTA of which fits into the registers the
-    // G kernel leaves free, and fills the idle issue slots and HBM bandwidth.
-    const bool both = view.n_simple > 0 && view.n_generic > 0 && (class_mask & 3) == 3;
-    const bool overlap = both && side && side->stream && n >= 64;
+    // is launched first; the OPAQUE/U kernel (write bound) follows on the low-priority side stream in its 128-thread
+    // shape, one CTA of which fits into the registers the G kernel leaves free, and fills the idle issue slots and HBM
+    // bandwidth.
+    const bool both = view.n_simple > 0 && view.n_generic > 0 && (L.class_mask & 3) == 3;
+    const bool overlap = both && L.side && L.side->stream && n >= 64;
     auto       launch_simple = [&](cudaStream_t st, bool small) -> cudaError_t {
         const unsigned tiles = (unsigned)(view.n_simple / 32);
         for(int first = 0; first < n; first += 65535 * kSimpleImages) {
@@ -654,28 +617,45 @@ cudaError_t launch_k2(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, 
     };
     auto launch_generic = [&]() -> cudaError_t {
         cudaError_t ge;
+        const int   sms = L.sm_count > 0 ? L.sm_count : 148;
+        if(use_tc) {
+            // tensor-core kernel; with the range check (tc == 1) the fp32 kernel follows as a redo pass that exits at once
+            // when no block was out of range
+            const bool check = L.tc == 1;
+            if((ge = cudaMemsetAsync(p.counter, 0, check ? k2_scratch_bytes(n, view) : 256, s)) != cudaSuccess) return ge;
+            if((ge = launch_k2_generic_tc(s, p, sms, check, &dev->tc_attr)) != cudaSuccess) return ge;
+            if(launches) (*launches)++;
+            if(check) {
+                const long long nitems = (long long)(view.n_generic / 32) * ((n + p.images_per_item - 1) / p.images_per_item);
+                if(nitems > 0x7fffffffLL) return cudaErrorInvalidValue;
+                const int ctas = nitems < (long long)sms * ctas_per_sm ? (int)nitems : sms * ctas_per_sm;
+                k2_generic_kernel<g_warps, 3, true><<<ctas, g_warps * 32, g_smem(g_warps), s>>>(p);
+                if((ge = cudaGetLastError()) != cudaSuccess) return ge;
+                if(launches) (*launches)++;
+            }
+            return cudaSuccess;
+        }
         if((ge = cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), s)) != cudaSuccess) return ge;
         const long long nitems = (long long)(view.n_generic / 32) * ((n + p.images_per_item - 1) / p.images_per_item);
         if(nitems > 0x7fffffffLL) return cudaErrorInvalidValue;
-        const int sms = sm_count > 0 ? sm_count : 148;
         const int ctas = nitems < (long long)sms * ctas_per_sm ? (int)nitems : sms * ctas_per_sm;
-        k2_generic_kernel<g_warps, 3><<<ctas, g_warps * 32, g_smem(g_warps), s>>>(p);
+        k2_generic_kernel<g_warps, 3, false><<<ctas, g_warps * 32, g_smem(g_warps), s>>>(p);
         if((ge = cudaGetLastError()) != cudaSuccess) return ge;
         if(launches) (*launches)++;
         return cudaSuccess;
     };
     if(overlap) {
-        if((e = cudaEventRecord(side->fork, s)) != cudaSuccess) return e;
-        if((e = cudaStreamWaitEvent(side->stream, side->fork, 0)) != cudaSuccess) return e;
+        if((e = cudaEventRecord(L.side->fork, s)) != cudaSuccess) return e;
+        if((e = cudaStreamWaitEvent(L.side->stream, L.side->fork, 0)) != cudaSuccess) return e;
         if((e = launch_generic()) != cudaSuccess) return e;
-        if((e = launch_simple(side->stream, true)) != cudaSuccess) return e;
-        if((e = cudaEventRecord(side->join, side->stream)) != cudaSuccess) return e;
-        if((e = cudaStreamWaitEvent(s, side->join, 0)) != cudaSuccess) return e;
+        if((e = launch_simple(L.side->stream, true)) != cudaSuccess) return e;
+        if((e = cudaEventRecord(L.side->join, L.side->stream)) != cudaSuccess) return e;
+        if((e = cudaStreamWaitEvent(s, L.side->join, 0)) != cudaSuccess) return e;
         return cudaSuccess;
     }
-    if(view.n_simple > 0 && (class_mask & 1))
+    if(view.n_simple > 0 && (L.class_mask & 1))
         if((e = launch_simple(s, false)) != cudaSuccess) return e;
-    if(view.n_generic > 0 && (class_mask & 2))
+    if(view.n_generic > 0 && (L.class_mask & 2))
         if((e = launch_generic()) != cudaSuccess) return e;
     return cudaSuccess;
 }

@@ -105,6 +105,7 @@ int mjx_ctx_create(mjx_ctx **out, int device) {
     }
     ctx->stream = ctx->own_stream;
     if(const char *ev = getenv("MJX_K2_OVERLAP")) ctx->overlap = atoi(ev) != 0;
+    if(const char *ev = getenv("MJX_K2_TC")) ctx->k2_tc = atoi(ev) < 0 ? 0 : (atoi(ev) > 2 ? 2 : atoi(ev));
     *out = ctx;
     return MJX_OK;
 }
@@ -352,13 +353,15 @@ static int dropon_finish(mjx_ctx *ctx, mjx_dropon *d) {
     off = align_up(off + n_generic * 256, 256);
     const size_t off_a = off;
     off = align_up(off + n_generic * 256, 256);
+    const size_t off_ad = off;
+    off = align_up(off + n_generic * 256, 256);
     d->slab2_bytes = off ? off : 256;
     e = cudaMallocAsync(&d->slab2, d->slab2_bytes, ctx->stream);
     if(e != cudaSuccess) return fail(ctx, e, "cudaMallocAsync(compiled dropon lists)");
     char *base = (char *)d->slab2;
     if(n_generic) { // padding slots: entry 0xffffffff, A = Ds = 0
         e = cudaMemsetAsync(base + off_lg, 0xff, n_generic * sizeof(uint32_t), ctx->stream);
-        if(e == cudaSuccess) e = cudaMemsetAsync(base + off_ds, 0, n_generic * 512, ctx->stream);
+        if(e == cudaSuccess) e = cudaMemsetAsync(base + off_ds, 0, n_generic * 768, ctx->stream);
         if(e != cudaSuccess) return fail(ctx, e, "clear generic list");
     }
     if(n_simple) {
@@ -371,6 +374,7 @@ static int dropon_finish(mjx_ctx *ctx, mjx_dropon *d) {
     d->view.n_generic = (int)n_generic;
     d->view.gDs = (const float *)(base + off_ds);
     d->view.gA = (const float *)(base + off_a);
+    d->view.gAd = (const float *)(base + off_ad);
     int launches = 0;
     e = launch_build_lists(ctx->stream, d, (uint32_t *)(base + off_chunks), &launches);
     ctx->launches += launches;
@@ -583,6 +587,12 @@ int mjx_ctx_set_zero_copy(mjx_ctx *ctx, int on) {
     return MJX_OK;
 }
 
+int mjx_ctx_set_tensor_core(mjx_ctx *ctx, int mode) {
+    if(!ctx || mode < 0 || mode > 2) return MJX_ERR_ARG;
+    ctx->k2_tc = mode;
+    return MJX_OK;
+}
+
 int mjx_ctx_set_strict(mjx_ctx *ctx, int strict) {
     if(!ctx) return MJX_ERR_ARG;
     ctx->strict = strict ? 1 : 0;
@@ -593,18 +603,38 @@ int mjx_ctx_set_strict(mjx_ctx *ctx, int strict) {
 // K2 entry points
 // ---------------------------------------------------------------------------------------
 
+} // extern "C"
+
+// one K2 launch with the ctx's settings on stream `st`; `scratch` holds k2_scratch_bytes(n, view) bytes
+static cudaError_t run_k2(mjx_ctx *ctx, cudaStream_t st, void *scratch, const mjx_image_desc_t *items_dev, int n, const mjx_dropon *d,
+                          int block_x, int block_y, bool with_side) {
+    const K2Side side = {ctx->side_stream, ctx->side_fork, ctx->side_join};
+    int          launches = 0;
+    K2Launch     L;
+    L.stream = st;
+    L.scratch = scratch;
+    L.strict = ctx->strict;
+    L.sm_count = ctx->sm_count;
+    L.class_mask = ctx->class_mask;
+    L.tc = ctx->k2_tc;
+    L.side = with_side && ctx->overlap ? &side : nullptr;
+    L.dev = &ctx->k2dev;
+    L.launches = &launches;
+    const cudaError_t e = launch_k2(L, items_dev, n, d->view, block_x, block_y);
+    ctx->launches += launches;
+    return e;
+}
+
+extern "C" {
+
 int mjx_compose_batch_device(mjx_ctx *ctx, const mjx_image_desc_t *items_dev, int n, const mjx_dropon *d, int block_x,
                              int block_y) {
     int rv = use_device(ctx);
     if(rv) return rv;
     if(!items_dev || !d || n < 0 || block_x < 0 || block_y < 0) return MJX_ERR_ARG;
     if(d->device != ctx->device) return MJX_ERR_ARG;
-    if((rv = ensure_scratch(ctx, k2_scratch_bytes())) != MJX_OK) return rv;
-    int         launches = 0;
-    const K2Side side = {ctx->side_stream, ctx->side_fork, ctx->side_join};
-    cudaError_t  e = launch_k2(ctx->stream, items_dev, n, d->view, block_x, block_y, ctx->scratch, ctx->strict, ctx->sm_count, ctx->class_mask, &launches,
-                               ctx->overlap ? &side : nullptr);
-    ctx->launches += launches;
+    if((rv = ensure_scratch(ctx, k2_scratch_bytes(n, d->view))) != MJX_OK) return rv;
+    const cudaError_t e = run_k2(ctx, ctx->stream, ctx->scratch, items_dev, n, d, block_x, block_y, true);
     if(e != cudaSuccess) return fail(ctx, e, "k2_compose_kernel");
     return MJX_OK;
 }
@@ -641,10 +671,8 @@ int mjx_compose_rows_host(mjx_ctx *ctx, int ncomp, int16_t *const *const *rows, 
     }
     MJX_CUDA(ctx, cudaMemcpyAsync(dev, pin, total, cudaMemcpyHostToDevice, ctx->stream));
     // the staged region starts at the dropon's origin: MCU position (0, 0)
-    if((rv = ensure_scratch(ctx, k2_scratch_bytes())) != MJX_OK) return rv;
-    int         launches = 0;
-    cudaError_t e = launch_k2(ctx->stream, (const mjx_image_desc_t *)dev, 1, d->view, 0, 0, ctx->scratch, ctx->strict, ctx->sm_count, ctx->class_mask, &launches);
-    ctx->launches += launches;
+    if((rv = ensure_scratch(ctx, k2_scratch_bytes(1, d->view))) != MJX_OK) return rv;
+    const cudaError_t e = run_k2(ctx, ctx->stream, ctx->scratch, (const mjx_image_desc_t *)dev, 1, d, 0, 0, false);
     if(e != cudaSuccess) return fail(ctx, e, "k2_compose_kernel");
     const size_t head = align_up(sizeof(mjx_image_desc_t), 256);
     MJX_CUDA(ctx, cudaMemcpyAsync(pin + head, dev + head, total - head, cudaMemcpyDeviceToHost, ctx->stream));
@@ -696,7 +724,7 @@ int mjx_compose_batch_host(mjx_ctx *ctx, const mjx_host_image_t *items, int n, c
         if(mapped) {
             const size_t dbytes = sizeof(mjx_image_desc_t) * (size_t)n;
             if((rv = ensure_pin(ctx, dbytes)) || (rv = ensure_desc(ctx, dbytes)) ||
-               (rv = ensure_scratch(ctx, k2_scratch_bytes())))
+               (rv = ensure_scratch(ctx, k2_scratch_bytes(n, d->view))))
                 return rv;
             mjx_image_desc_t *desc = (mjx_image_desc_t *)ctx->pin;
             memset(desc, 0, dbytes);
@@ -712,11 +740,7 @@ int mjx_compose_batch_host(mjx_ctx *ctx, const mjx_host_image_t *items, int n, c
                     memcpy(desc[i].q[c], items[i].q[c], 128);
                 }
             MJX_CUDA(ctx, cudaMemcpyAsync(ctx->desc_dev, desc, dbytes, cudaMemcpyHostToDevice, ctx->stream));
-            int         launches = 0;
-            const K2Side side = {ctx->side_stream, ctx->side_fork, ctx->side_join};
-            cudaError_t  e = launch_k2(ctx->stream, (const mjx_image_desc_t *)ctx->desc_dev, n, d->view, block_x, block_y, ctx->scratch,
-                                       ctx->strict, ctx->sm_count, ctx->class_mask, &launches, ctx->overlap ? &side : nullptr);
-            ctx->launches += launches;
+            const cudaError_t e = run_k2(ctx, ctx->stream, ctx->scratch, (const mjx_image_desc_t *)ctx->desc_dev, n, d, block_x, block_y, true);
             if(e != cudaSuccess) return fail(ctx, e, "k2_compose_kernel");
             MJX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             return MJX_OK;
@@ -730,7 +754,7 @@ int mjx_compose_batch_host(mjx_ctx *ctx, const mjx_host_image_t *items, int n, c
     }
     const int    P = mjx_ctx::kPipe;
     const size_t desc_sz = align_up(sizeof(mjx_image_desc_t), 256);
-    const size_t scr_sz = align_up(k2_scratch_bytes(), 256);
+    const size_t scr_sz = align_up(k2_scratch_bytes(1, d->view), 256);
     if((rv = pipe_init(ctx)) || (rv = ensure_dev(ctx, slot * P)) || (rv = ensure_desc(ctx, desc_sz * P)) || (rv = ensure_scratch(ctx, scr_sz * P)) ||
        (rv = ensure_pin(ctx, desc_sz * (size_t)n)))
         return rv;
@@ -766,10 +790,7 @@ int mjx_compose_batch_host(mjx_ctx *ctx, const mjx_host_image_t *items, int n, c
             if(sp == wbytes) MJX_CUDA(ctx, cudaMemcpyAsync(base + off[c], src, wbytes * dc.hb, cudaMemcpyHostToDevice, st));
             else MJX_CUDA(ctx, cudaMemcpy2DAsync(base + off[c], wbytes, src, sp, wbytes, dc.hb, cudaMemcpyHostToDevice, st));
         }
-        int         launches = 0;
-        cudaError_t e = launch_k2(st, (const mjx_image_desc_t *)(ddev + desc_sz * s), 1, d->view, 0, 0, (char *)ctx->scratch + scr_sz * s,
-                                  ctx->strict, ctx->sm_count, ctx->class_mask, &launches);
-        ctx->launches += launches;
+        const cudaError_t e = run_k2(ctx, st, (char *)ctx->scratch + scr_sz * s, (const mjx_image_desc_t *)(ddev + desc_sz * s), 1, d, 0, 0, false);
         if(e != cudaSuccess) return fail(ctx, e, "k2_compose_kernel");
         for(int c = 0; c < ncomp; c++) {
             const DropComp &dc = d->view.comp[c];

@@ -37,6 +37,7 @@ struct DropView {
     int             stile_start[MJX_MAX_COMPONENTS]; // ... in list_simple
     const float    *gDs; // [n_generic][64] overlay coefficients * IDCT prescale (natural order)
     const float    *gA;  // [n_generic][64] pixel-domain alpha / 255 = IDCT2(W) / 255, stored Q-paired: (8i + k)*2 + h = A[2i + h][k]
+    const float    *gAd; // [n_generic][64] A o IDCT2(D): alpha times the overlay's pixels (minus 128), Q-paired like gA
 };
 
 static inline __host__ __device__ uint32_t entry_pack(int comp, int row, int col) {
@@ -46,6 +47,14 @@ static inline __host__ __device__ int entry_comp(uint32_t e) { return (int)(e >>
 static inline __host__ __device__ int entry_row(uint32_t e) { return (int)((e >> 15) & 0x7fffu); }
 static inline __host__ __device__ int entry_col(uint32_t e) { return (int)(e & 0x7fffu); }
 
+} // namespace mjx
+
+namespace mjx {
+// what a ctx remembers about its device between K2 launches (function attributes are per device)
+struct K2Dev {
+    bool g_attr = false, tc_attr = false;
+    int  g_ctas_per_sm = 0;
+};
 } // namespace mjx
 
 // ---- opaque handles -------------------------------------------------------------------
@@ -97,6 +106,8 @@ struct mjx_ctx {
     cudaStream_t side_stream = nullptr;
     cudaEvent_t  side_fork = nullptr, side_join = nullptr;
     int          overlap = 1;
+    int          k2_tc = 1; // G class on the tensor-core kernel (batches of >= kTcMinImages images): 1 with range check, 2 without, 0 off
+    mjx::K2Dev   k2dev;
 };
 
 namespace mjx {
@@ -106,9 +117,6 @@ int  ensure_pin(mjx_ctx *ctx, size_t bytes);
 int  ensure_dev(mjx_ctx *ctx, size_t bytes);
 int  ensure_desc(mjx_ctx *ctx, size_t bytes);
 int  ensure_scratch(mjx_ctx *ctx, size_t bytes);
-
-// bytes of scratch one K2 launch needs (the work counter)
-size_t k2_scratch_bytes();
 
 // kernel launchers (each returns a cudaError_t from the launch; *launches += kernels launched)
 cudaError_t launch_k1(cudaStream_t s, const uint8_t *image3, const uint8_t *alpha3, int dw, int dh, int dropon_cs,
@@ -123,9 +131,21 @@ struct K2Side {
     cudaStream_t stream;
     cudaEvent_t  fork, join;
 };
-cudaError_t launch_k2(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, const DropView &view, int block_x,
-                      int block_y, void *scratch, int strict, int sm_count, int class_mask, int *launches,
-                      const K2Side *side = nullptr);
+struct K2Launch {
+    cudaStream_t  stream = nullptr;
+    void         *scratch = nullptr; // k2_scratch_bytes(n, view) bytes
+    int           strict = 0;
+    int           sm_count = 0;
+    int           class_mask = 3;
+    int           tc = 0;            // G class: 0 fp32 kernel; 1 tensor-core kernel, coefficient range checked (out-of-range
+                                     // blocks go to the fp32 kernel); 2 tensor-core kernel, range vouched for by the caller
+    const K2Side *side = nullptr;
+    K2Dev        *dev = nullptr;
+    int          *launches = nullptr;
+};
+// bytes of scratch one K2 launch over n images needs (work counters + the redo bitmap of the tensor-core kernel)
+size_t      k2_scratch_bytes(int n, const DropView &view);
+cudaError_t launch_k2(const K2Launch &L, const mjx_image_desc_t *items_dev, int n, const DropView &view, int block_x, int block_y);
 // dc_compact (optional, n == 1): per component a device array [hreal][wreal] the rewrite kernel takes the DCs from
 cudaError_t launch_k3(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, int ncomp, const mjx_effect_op_t *ops,
                       int nops, int *launches, const int16_t *const *dc_compact = nullptr);
