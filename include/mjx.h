@@ -106,12 +106,20 @@ int         mjx_ctx_use_own_stream(mjx_ctx *ctx);                /* back to the 
 /* strict = 1: K2 runs as one kernel that reproduces the reference's int16 wrap-around on out-of-range
  * products (adversarial streams); default 0: the fast kernels, identical on every encoder-produced JPEG */
 int         mjx_ctx_set_strict(mjx_ctx *ctx, int strict);
-/* class G blocks (non-uniform alpha) of batches: the inverse transform runs on the tensor cores (tcgen05, fp16 operands,
- * fp32 accumulation; libmodjpeg_b200/csrc/k2_generic_tc.cu).  Its integer operand trick needs every coefficient in the
- * baseline range [-1024, 1023] (DC 11 bits, AC 10 bits: what ITU-T T.81 allows an 8-bit JPEG to carry).
- * mode 1 (default): the kernel checks that per block and hands blocks outside the range to the fp32 kernel;
- * mode 2: no check, the caller vouches for the range; mode 0: fp32 kernel only.  Env MJX_K2_TC sets the initial mode. */
+/* class G blocks (non-uniform alpha) of batches of >= 256 images: the blend runs as one tensor-core product per dropon
+ * block and 128 images (tcgen05, fp16 operands, fp32 accumulation; libmodjpeg_b200/csrc/k2_generic_op.cu) -- what
+ * mj_compose_with_mask + mj_convolve compute per block is linear in the image block (reference: src/compose.c:289-312),
+ * and its 64 x 64 operator is built once per (compiled dropon, quantisation tables) and cached in the dropon.  The integer
+ * operand needs every coefficient in the baseline range [-1024, 1023] (DC 11 bits, AC 10 bits: what ITU-T T.81 allows an
+ * 8-bit JPEG to carry) and quantiser values <= 255.
+ * mode 1 (default): the kernel checks the range per block and hands what is outside it, and images whose tables differ
+ * from the first image's, to the fp32 kernel; mode 2: no range check, the caller vouches for it; mode 0: fp32 kernel only.
+ * Env MJX_K2_TC sets the initial mode.  The cache (16 or 24 KB per class G block, MJX_K2_OP_MAX_MB caps it, default 4096)
+ * belongs to the first ctx that uses the dropon this way; other ctxs run the fp32 kernel with it. */
 int         mjx_ctx_set_tensor_core(mjx_ctx *ctx, int mode);
+/* fp16 pieces per operator entry: 2 (default, 22 significant bits) or 3 (33 bits); takes effect for dropons whose cache
+ * has not been allocated yet.  Env MJX_K2_OP_PIECES sets the initial value. */
+int         mjx_ctx_set_operator_pieces(mjx_ctx *ctx, int pieces);
 /* on = 1 (default): mjx_compose_batch_host runs K2 directly on page-locked (GPU-addressable) host planes, so only
  * the blocks the dropon touches cross PCIe; 0: always stage the region under the dropon through device memory */
 int         mjx_ctx_set_zero_copy(mjx_ctx *ctx, int on);

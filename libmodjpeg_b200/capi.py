@@ -98,6 +98,7 @@ def load_mjx() -> C.CDLL:
     L.mjx_ctx_use_own_stream.argtypes = [vp]
     L.mjx_ctx_set_strict.argtypes = [vp, C.c_int]
     L.mjx_ctx_set_tensor_core.argtypes = [vp, C.c_int]
+    L.mjx_ctx_set_operator_pieces.argtypes = [vp, C.c_int]
     L.mjx_ctx_stream.argtypes = [vp]
     L.mjx_ctx_stream.restype = vp
     L.mjx_ctx_sync.argtypes = [vp]
@@ -260,8 +261,13 @@ class Engine:
         self._check(self.lib.mjx_ctx_set_overlap(self.ctx, 1 if on else 0), "mjx_ctx_set_overlap")
 
     def set_tensor_core(self, mode: int) -> None:
-        """G class of batches: 1 tensor-core kernel with coefficient range check (default), 2 without check, 0 fp32 kernel"""
+        """G class of batches of >= 256 images: 1 tensor-core kernel with coefficient range check (default), 2 without
+        check, 0 fp32 kernel"""
         self._check(self.lib.mjx_ctx_set_tensor_core(self.ctx, mode), "mjx_ctx_set_tensor_core")
+
+    def set_operator_pieces(self, pieces: int) -> None:
+        """fp16 pieces per entry of the tensor-core kernel's operator (2 or 3); for dropons not yet used in a large batch"""
+        self._check(self.lib.mjx_ctx_set_operator_pieces(self.ctx, pieces), "mjx_ctx_set_operator_pieces")
 
     def set_strict(self, strict: bool) -> None:
         """strict: one K2 kernel with the reference's int16 wrap-around (adversarial inputs); default fast kernels"""

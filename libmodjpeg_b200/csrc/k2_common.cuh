@@ -13,13 +13,43 @@ struct FastParams {
     int                     n;       // images
     int                     block_x, block_y;
     int                     images_per_item;
-    // tensor-core G kernel with range check: (tile, image) pairs it leaves to the fp32 kernel -- bit tile * n + image
-    unsigned int           *redo_bits;
+    // blocks the tensor-core G kernel left to the fp32 kernel: word tile * n + image, bit = slot within the tile
+    unsigned int           *redo_mask;
     unsigned int           *redo_count;
 };
 
-// launcher of the tensor-core G kernel (k2_generic_tc.cu); *attr_set caches the per-device function attribute
-cudaError_t launch_k2_generic_tc(cudaStream_t s, const FastParams &p, int sm_count, bool check, bool *attr_set);
+// ---- the tensor-core G kernel of large batches (k2_generic_op.cu) ---------------------------------------------------
+static constexpr int kOpGroups = 4; // groups of four warps per CTA, one 128-image UMMA in flight each
+
+// device pointers into the operator cache of a compiled dropon
+struct OpView {
+    unsigned char *B;       // [n_generic][np][8192] operator pieces, fp16, stored as SWIZZLE_128B shared-memory images
+    float         *K;       // [n_generic][64] L(D): the overlay's share of the blend term
+    unsigned char *diag;    // [MJX_MAX_COMPONENTS][8192] diag(q) half of the first piece's tile
+    float         *rq;      // [MJX_MAX_COMPONENTS][64] biased reciprocals of the tables
+    uint16_t      *key;     // [MJX_MAX_COMPONENTS][64] the tables the cache was built for
+    int           *info;    // [MJX_MAX_COMPONENTS] log2 of the operator's scale, -1: component not served (q > 255)
+    int           *rebuild; // [MJX_MAX_COMPONENTS] set by the prepare kernel when the tables changed
+    int            np;      // fp16 pieces per operator entry (2 or 3)
+};
+
+struct OpParams {
+    DropView                drop;
+    OpView                  op;
+    const mjx_image_desc_t *items;
+    uint4                  *table; // [ncomp][n] plane address, stride, rows of the images that take this path
+    unsigned int           *redo_mask;
+    unsigned int           *redo_count;
+    int                     n;
+    int                     block_x, block_y;
+};
+
+// bytes of the operator cache of a dropon with n_generic list slots; with v != nullptr: v->B holds the slab's base on
+// entry and every pointer of *v is set on return
+size_t      op_cache_bytes(int n_generic, int np, OpView *v);
+// prepare (address table, table comparison) + operator build (no-op when the tables are unchanged) + the kernel;
+// attr_set[2] caches the per-device function attributes
+cudaError_t launch_k2_generic_op(cudaStream_t s, const OpParams &p, int sm_count, bool check, bool *attr_set, int *launches);
 
 static constexpr int kGStages = 2;
 // Shared-memory blocks are PADDED by one 16-byte chunk (stride 144 B for int16 blocks, 272 B for

@@ -305,9 +305,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k2_simple_kernel(cons
 // scalar adds per pass instead of a register transpose.  ~1.5 k issue slots per block (the
 // scalar fp32 version needed ~2.3 k); measured balance and what limits it: DESIGN.md 4.2.
 
-// kRedo: second pass behind the tensor-core kernel -- only the (tile, image) pairs whose bit is set in p.redo_bits are
-// processed (blocks with coefficients outside the baseline range, which that kernel left alone); exits at once when
-// the count is zero.
+// kRedo: second pass behind the tensor-core kernel -- only the blocks whose bit is set in p.redo_mask are processed
+// (coefficients outside the baseline range, images with other quantisation tables: what that kernel left alone);
+// exits at once when the count is zero.
 template <int kGWarps, int kMinCtas, bool kRedo>
 __global__ void __launch_bounds__(kGWarps * 32, kMinCtas) k2_generic_kernel(const FastParams p) {
     constexpr int kGThreads = kGWarps * 32;
@@ -387,8 +387,8 @@ __global__ void __launch_bounds__(kGWarps * 32, kMinCtas) k2_generic_kernel(cons
             unsigned long long       a = 0;
             if(my_valid && my_row < rows && my_col < stride) a = plane + ((unsigned long long)my_row * stride + my_col) * 128ull;
             if(kRedo) {
-                const long long bit = (long long)cur_tile * p.n + (i0 + k * kGWarps);
-                if(!((__ldg(p.redo_bits + (bit >> 5)) >> (bit & 31)) & 1u)) a = 0;
+                const unsigned m = __ldg(p.redo_mask + (size_t)cur_tile * p.n + (i0 + k * kGWarps));
+                if(!((m >> lane) & 1u)) a = 0;
             }
             addr[lane] = a;
             const bool all_there = __all_sync(0xffffffffu, a != 0); // the usual case: every block of the tile lies on this image
@@ -536,14 +536,14 @@ cudaError_t launch_selftest_reciprocal(cudaStream_t s, unsigned long long *misma
 // launcher
 // =========================================================================================
 
-static constexpr int kTcMinImages = 24; // below this the 12-warp CTAs of the tensor-core kernel run mostly empty
-
-static size_t redo_bitmap_bytes(int n, const DropView &view) {
-    const long long bits = (long long)(view.n_generic / 32) * (n > 0 ? n : 0);
-    return (size_t)((bits + 31) / 32 * 4 + 255) / 256 * 256;
+static size_t redo_mask_bytes(int n, const DropView &view) { return ((size_t)(view.n_generic / 32) * (size_t)(n > 0 ? n : 0) * 4 + 255) / 256 * 256; }
+// [0] work counter of the G kernel, [1] redo count, [2] work counter of the redo pass; from byte 256 on, for batches the
+// tensor-core kernel may serve: the redo mask (one word per tile and image), then its address table (16 bytes per
+// component and image)
+size_t k2_scratch_bytes(int n, const DropView &view) {
+    if(n < kOpMinImages || view.n_generic == 0) return 256;
+    return 256 + redo_mask_bytes(n, view) + (size_t)MJX_MAX_COMPONENTS * n * 16;
 }
-// [0] work counter of the G kernel, [1] redo count, [2] work counter of the redo pass, [64..] redo bitmap
-size_t k2_scratch_bytes(int n, const DropView &view) { return 256 + redo_bitmap_bytes(n, view); }
 
 cudaError_t launch_k2(const K2Launch &L, const mjx_image_desc_t *items_dev, int n, const DropView &view, int block_x, int block_y) {
     if(n <= 0 || view.total_blocks <= 0) return cudaSuccess;
@@ -581,13 +581,13 @@ cudaError_t launch_k2(const K2Launch &L, const mjx_image_desc_t *items_dev, int 
         dev->g_attr = true;
     }
     const int ctas_per_sm = dev->g_ctas_per_sm;
-    const bool use_tc = L.tc != 0 && n >= kTcMinImages && view.n_generic > 0 && (L.class_mask & 2);
+    const bool use_op = L.tc != 0 && L.op != nullptr && n >= kOpMinImages && view.n_generic > 0 && (L.class_mask & 2);
     FastParams p;
     p.drop = view;
     p.items = items_dev;
     p.counter = reinterpret_cast<unsigned int *>(L.scratch);
     p.redo_count = p.counter + 1;
-    p.redo_bits = p.counter + 64;
+    p.redo_mask = p.counter + 64;
     p.n = n;
     p.block_x = block_x;
     p.block_y = block_y;
@@ -618,21 +618,28 @@ cudaError_t launch_k2(const K2Launch &L, const mjx_image_desc_t *items_dev, int 
     auto launch_generic = [&]() -> cudaError_t {
         cudaError_t ge;
         const int   sms = L.sm_count > 0 ? L.sm_count : 148;
-        if(use_tc) {
-            // tensor-core kernel; with the range check (tc == 1) the fp32 kernel follows as a redo pass that exits at once
-            // when no block was out of range
-            const bool check = L.tc == 1;
-            if((ge = cudaMemsetAsync(p.counter, 0, check ? k2_scratch_bytes(n, view) : 256, s)) != cudaSuccess) return ge;
-            if((ge = launch_k2_generic_tc(s, p, sms, check, &dev->tc_attr)) != cudaSuccess) return ge;
+        if(use_op) {
+            // tensor-core kernel; the fp32 kernel follows as a redo pass over what that kernel left alone (coefficients
+            // outside the baseline range when checked, images with other quantisation tables) and exits at once when
+            // there is nothing
+            if((ge = cudaMemsetAsync(p.counter, 0, 256 + redo_mask_bytes(n, view), s)) != cudaSuccess) return ge;
+            OpParams op;
+            op.drop = view;
+            op.op = *L.op;
+            op.items = items_dev;
+            op.table = reinterpret_cast<uint4 *>(reinterpret_cast<char *>(L.scratch) + 256 + redo_mask_bytes(n, view));
+            op.redo_mask = p.redo_mask;
+            op.redo_count = p.redo_count;
+            op.n = n;
+            op.block_x = block_x;
+            op.block_y = block_y;
+            if((ge = launch_k2_generic_op(s, op, sms, L.tc == 1, dev->op_attr, launches)) != cudaSuccess) return ge;
+            const long long nitems = (long long)(view.n_generic / 32) * ((n + p.images_per_item - 1) / p.images_per_item);
+            if(nitems > 0x7fffffffLL) return cudaErrorInvalidValue;
+            const int ctas = nitems < (long long)sms * ctas_per_sm ? (int)nitems : sms * ctas_per_sm;
+            k2_generic_kernel<g_warps, 3, true><<<ctas, g_warps * 32, g_smem(g_warps), s>>>(p);
+            if((ge = cudaGetLastError()) != cudaSuccess) return ge;
             if(launches) (*launches)++;
-            if(check) {
-                const long long nitems = (long long)(view.n_generic / 32) * ((n + p.images_per_item - 1) / p.images_per_item);
-                if(nitems > 0x7fffffffLL) return cudaErrorInvalidValue;
-                const int ctas = nitems < (long long)sms * ctas_per_sm ? (int)nitems : sms * ctas_per_sm;
-                k2_generic_kernel<g_warps, 3, true><<<ctas, g_warps * 32, g_smem(g_warps), s>>>(p);
-                if((ge = cudaGetLastError()) != cudaSuccess) return ge;
-                if(launches) (*launches)++;
-            }
             return cudaSuccess;
         }
         if((ge = cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), s)) != cudaSuccess) return ge;

@@ -8,6 +8,7 @@
 
 #include "mjx_internal.cuh"
 #include "mjx_math.cuh"
+#include "k2_common.cuh"
 
 namespace mjx {
 
@@ -106,6 +107,8 @@ int mjx_ctx_create(mjx_ctx **out, int device) {
     ctx->stream = ctx->own_stream;
     if(const char *ev = getenv("MJX_K2_OVERLAP")) ctx->overlap = atoi(ev) != 0;
     if(const char *ev = getenv("MJX_K2_TC")) ctx->k2_tc = atoi(ev) < 0 ? 0 : (atoi(ev) > 2 ? 2 : atoi(ev));
+    if(const char *ev = getenv("MJX_K2_OP_PIECES")) ctx->k2_op_pieces = atoi(ev) >= 3 ? 3 : 2;
+    if(const char *ev = getenv("MJX_K2_OP_MAX_MB")) ctx->k2_op_max_bytes = (size_t)(atoll(ev) > 0 ? atoll(ev) : 0) << 20;
     *out = ctx;
     return MJX_OK;
 }
@@ -500,6 +503,8 @@ void mjx_dropon_free(mjx_dropon *d) {
     // pool only hands the block to another stream once this free has been reached
     if(d->slab) cudaFreeAsync(d->slab, cudaStreamPerThread);
     if(d->slab2) cudaFreeAsync(d->slab2, cudaStreamPerThread);
+    if(d->op_slab) cudaFree(d->op_slab);
+    delete d->op;
     cudaGetLastError();
     delete d;
 }
@@ -593,6 +598,12 @@ int mjx_ctx_set_tensor_core(mjx_ctx *ctx, int mode) {
     return MJX_OK;
 }
 
+int mjx_ctx_set_operator_pieces(mjx_ctx *ctx, int pieces) {
+    if(!ctx || (pieces != 2 && pieces != 3)) return MJX_ERR_ARG;
+    ctx->k2_op_pieces = pieces;
+    return MJX_OK;
+}
+
 int mjx_ctx_set_strict(mjx_ctx *ctx, int strict) {
     if(!ctx) return MJX_ERR_ARG;
     ctx->strict = strict ? 1 : 0;
@@ -604,6 +615,35 @@ int mjx_ctx_set_strict(mjx_ctx *ctx, int strict) {
 // ---------------------------------------------------------------------------------------
 
 } // extern "C"
+
+// the dropon's operator cache for the tensor-core G kernel, if this ctx may use it (allocated on first use)
+static const OpView *dropon_op_cache(mjx_ctx *ctx, const mjx_dropon *cd, int n) {
+    mjx_dropon *d = const_cast<mjx_dropon *>(cd); // the cache is the one mutable part of a compiled dropon
+    if(!ctx->k2_tc || ctx->strict || n < kOpMinImages || d->view.n_generic <= 0) return nullptr;
+    mjx_ctx *none = nullptr;
+    if(d->op_owner.compare_exchange_strong(none, ctx)) {
+        const size_t bytes = op_cache_bytes(d->view.n_generic, ctx->k2_op_pieces, nullptr);
+        void        *slab = nullptr;
+        if(bytes <= ctx->k2_op_max_bytes && cudaMalloc(&slab, bytes) == cudaSuccess) {
+            OpView *v = new(std::nothrow) OpView();
+            if(v) {
+                v->B = (unsigned char *)slab;
+                op_cache_bytes(d->view.n_generic, ctx->k2_op_pieces, v);
+                // key = 0 never equals a real table: the first launch builds the operator
+                const size_t tail = (size_t)((char *)v->key - (char *)slab);
+                if(cudaMemsetAsync(v->key, 0, bytes - tail, ctx->stream) == cudaSuccess) {
+                    d->op_slab = slab;
+                    d->op_bytes = bytes;
+                    d->op = v;
+                }
+                else delete v;
+            }
+            if(!d->op) cudaFree(slab);
+        }
+        cudaGetLastError(); // an allocation failure only means the fp32 kernel runs
+    }
+    return d->op_owner.load() == ctx ? d->op : nullptr;
+}
 
 // one K2 launch with the ctx's settings on stream `st`; `scratch` holds k2_scratch_bytes(n, view) bytes
 static cudaError_t run_k2(mjx_ctx *ctx, cudaStream_t st, void *scratch, const mjx_image_desc_t *items_dev, int n, const mjx_dropon *d,
@@ -617,6 +657,7 @@ static cudaError_t run_k2(mjx_ctx *ctx, cudaStream_t st, void *scratch, const mj
     L.sm_count = ctx->sm_count;
     L.class_mask = ctx->class_mask;
     L.tc = ctx->k2_tc;
+    L.op = with_side ? dropon_op_cache(ctx, d, n) : nullptr; // batch entry points only
     L.side = with_side && ctx->overlap ? &side : nullptr;
     L.dev = &ctx->k2dev;
     L.launches = &launches;

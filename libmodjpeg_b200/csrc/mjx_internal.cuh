@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -52,9 +53,14 @@ static inline __host__ __device__ int entry_col(uint32_t e) { return (int)(e & 0
 namespace mjx {
 // what a ctx remembers about its device between K2 launches (function attributes are per device)
 struct K2Dev {
-    bool g_attr = false, tc_attr = false;
+    bool g_attr = false;
+    bool op_attr[2] = {false, false};
     int  g_ctas_per_sm = 0;
 };
+// batches of at least this many images take the tensor-core G kernel (k2_generic_op.cu): below it the operator pieces
+// (16-24 KB per dropon block and launch) outweigh what the fp32 kernel costs
+static constexpr int kOpMinImages = 256;
+struct OpView;
 } // namespace mjx
 
 // ---- opaque handles -------------------------------------------------------------------
@@ -72,6 +78,13 @@ struct mjx_dropon {
     long long      counts[4] = {}; // blocks per class, all components
     int            generic_pad[MJX_MAX_COMPONENTS] = {}; // padding slots before each component's part of the generic list
     int            simple_pad[MJX_MAX_COMPONENTS] = {};  // ... of the simple list
+    // operator cache of the tensor-core G kernel (k2_generic_op.cu): allocated by the first ctx that runs a large batch
+    // with this dropon and used by that ctx only (the cache is rebuilt in stream order when the batch's quantisation
+    // tables change, so it cannot serve two streams at once); every other ctx takes the fp32 kernel
+    std::atomic<mjx_ctx *> op_owner{nullptr};
+    void                  *op_slab = nullptr;
+    size_t                 op_bytes = 0;
+    mjx::OpView           *op = nullptr;
 };
 
 struct mjx_ctx {
@@ -106,7 +119,9 @@ struct mjx_ctx {
     cudaStream_t side_stream = nullptr;
     cudaEvent_t  side_fork = nullptr, side_join = nullptr;
     int          overlap = 1;
-    int          k2_tc = 1; // G class on the tensor-core kernel (batches of >= kTcMinImages images): 1 with range check, 2 without, 0 off
+    int          k2_tc = 1; // G class of batches of >= kOpMinImages images on the tensor-core kernel: 1 with range check, 2 without, 0 off
+    int          k2_op_pieces = 2;     // fp16 pieces per operator entry (MJX_K2_OP_PIECES: 2 or 3)
+    size_t       k2_op_max_bytes = (size_t)4 << 30; // largest operator cache a dropon may get (MJX_K2_OP_MAX_MB)
     mjx::K2Dev   k2dev;
 };
 
@@ -137,8 +152,9 @@ struct K2Launch {
     int           strict = 0;
     int           sm_count = 0;
     int           class_mask = 3;
-    int           tc = 0;            // G class: 0 fp32 kernel; 1 tensor-core kernel, coefficient range checked (out-of-range
-                                     // blocks go to the fp32 kernel); 2 tensor-core kernel, range vouched for by the caller
+    int           tc = 0;            // G class of large batches: 0 fp32 kernel; 1 tensor-core kernel, coefficient range checked
+                                     // (out-of-range blocks go to the fp32 kernel); 2 tensor-core kernel, range vouched for
+    const OpView *op = nullptr;      // the dropon's operator cache (nullptr: not available, fp32 kernel)
     const K2Side *side = nullptr;
     K2Dev        *dev = nullptr;
     int          *launches = nullptr;
