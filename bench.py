@@ -40,6 +40,18 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 W_IMG, H_IMG = 1920, 1080
 N_BASES = 16
 ALIGN_TOP_LEFT = 4 | 1
+# both arms name the workload with the same words
+WORKLOAD = "c3: batch of 1920x1080 4:2:0 q85 JPEGs + full-frame tiled alpha logo, 48960 blocks/image (BASELINE.json configs[2])"
+
+
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
 
 
 def log(*a):
@@ -157,26 +169,105 @@ class CpuArm:
         dims = O.OraclePort().compiled_dims(O.make_layout(info["colorspace"], samp), g["blockoffset_x"], g["blockoffset_y"],
                                             g["crop_w"], g["crop_h"])
         self.blocks_per_image = sum(w * h for w, h in dims)
+        self.geom = g
+        self.image_blocks = sum(self.state[0][0].comp_info(c)["wreal"] * self.state[0][0].comp_info(c)["hreal"] for c in range(info["ncomp"]))
 
-    def step(self, images_per_thread: int = 1) -> float:
-        """compose images_per_thread images on every thread; returns wall seconds"""
+    def _run_threads(self, work, threads: int) -> float:
         errs = []
+
+        def guarded(t):
+            try:
+                work(t)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+
+        ts = [threading.Thread(target=guarded, args=(t,)) for t in range(threads)]
+        t0 = time.perf_counter()
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        dt = time.perf_counter() - t0
+        if errs:
+            raise RuntimeError(f"reference arm failed: {errs[:3]}")
+        return dt
+
+    def step(self, images_per_thread: int = 1, threads: int | None = None) -> float:
+        """mj_compose (dropon compile + blend, src/compose.c:33) of images_per_thread images on every thread; wall seconds"""
 
         def work(t):
             j, d = self.state[t]
             for _ in range(images_per_thread):
                 rv = j.compose(d, ALIGN_TOP_LEFT, 0, 0)
                 if rv != 0:
-                    errs.append(rv)
+                    raise RuntimeError(f"mj_compose -> {rv}")
 
-        ts = [threading.Thread(target=work, args=(t,)) for t in range(self.threads)]
-        t0 = time.perf_counter()
-        [t.start() for t in ts]
-        [t.join() for t in ts]
-        dt = time.perf_counter() - t0
-        if errs:
-            raise RuntimeError(f"reference mj_compose failed: {errs[:3]}")
-        return dt
+        return self._run_threads(work, threads or self.threads)
+
+    def split(self, images_per_thread: int, threads: int) -> dict:
+        """mj_compile_dropon (src/dropon.c:325) and mj_compose_with_mask (src/compose.c:237) timed separately, as
+        mj_compose calls them; per-thread seconds are summed per phase, rates are summed over the threads"""
+        g = self.geom
+        info, samp = self.state[0][0].info(), self.state[0][0].sampling()
+        comp_s, blend_s = [0.0] * threads, [0.0] * threads
+
+        def work(t):
+            j, d = self.state[t]
+            for _ in range(images_per_thread):
+                t0 = time.perf_counter()
+                rv, cd = self.lib.compile_handle(d, info["colorspace"], samp, g["blockoffset_x"], g["blockoffset_y"],
+                                                 (g["crop_x"], g["crop_y"], g["crop_w"], g["crop_h"]))
+                t1 = time.perf_counter()
+                if rv != 0:
+                    raise RuntimeError(f"mj_compile_dropon -> {rv}")
+                rv = self.lib.compose_with_mask(j, cd, g["block_x"], g["block_y"])
+                t2 = time.perf_counter()
+                self.lib.free_compiled(cd)
+                if rv != 0:
+                    raise RuntimeError(f"mj_compose_with_mask -> {rv}")
+                comp_s[t] += t1 - t0
+                blend_s[t] += t2 - t1
+
+        wall = self._run_threads(work, threads)
+        blocks = images_per_thread * self.blocks_per_image
+        return {"threads": threads, "images": images_per_thread * threads, "wall_s": wall,
+                "compile_ms_per_image": 1e3 * sum(comp_s) / (images_per_thread * threads),
+                "blend_ms_per_image": 1e3 * sum(blend_s) / (images_per_thread * threads),
+                "blend_only_mblocks_per_s": sum(blocks / b for b in blend_s if b > 0) / 1e6,
+                "compile_and_blend_mblocks_per_s": images_per_thread * threads * self.blocks_per_image / wall / 1e6}
+
+    def effects(self, threads: int, reps: int = 2) -> dict:
+        """each mj_effect_* (src/effect.c:28-222) on the decoded 1080p images, per-thread seconds summed"""
+        out = {}
+        nblocks = self.image_blocks
+        for name, call in (("luminance_40", lambda j: j.luminance(40)), ("tint_30_m30", lambda j: j.tint(30, -30)),
+                           ("pixelate", lambda j: j.pixelate()), ("grayscale", lambda j: j.grayscale())):
+            secs = [0.0] * threads
+
+            def work(t):
+                j = self.state[t][0]
+                for _ in range(reps):
+                    t0 = time.perf_counter()
+                    rv = call(j)
+                    secs[t] += time.perf_counter() - t0
+                    if rv != 0:
+                        raise RuntimeError(f"mj_effect {name} -> {rv}")
+
+            self._run_threads(work, threads)
+            out[name] = {"ms_per_image": 1e3 * sum(secs) / (reps * threads), "mblocks_per_s": sum(reps * nblocks / x for x in secs if x > 0) / 1e6}
+        return out
+
+    def baseline_report(self, reps: int = 2) -> dict:
+        """what BASELINE.md 3 / SURVEY 8d ask for: whole mj_compose, its two halves separately, each effect; one thread
+        and every host thread"""
+        T = self.threads
+        self.step(1, T)  # warm: page in, first-touch
+        rep = {"cpu_model": cpu_model(), "host_threads": T}
+        for label, th in (("1_thread", 1), (f"{T}_threads", T)):
+            dt = self.step(reps, th)
+            rep[label] = {"mj_compose_mblocks_per_s": th * reps * self.blocks_per_image / dt / 1e6,
+                          "mj_compose_images_per_s": th * reps / dt, "split": self.split(reps, th)}
+        rep["effects_1_thread"] = self.effects(1)
+        rep[f"effects_{T}_threads"] = self.effects(T)  # last: grayscale zeroes the chroma planes of the arm's images
+        return rep
 
 
 def reference_file_pipeline(jpegs, logo, threads: int, images: int) -> float:
@@ -227,15 +318,19 @@ def run_reference_arm(args, rank: int, world: int):
     images = threads * args.steps
     blocks = images * arm.blocks_per_image
     mbps = blocks / total / 1e6
+    detail = None
+    if not args.no_cpu_baseline:
+        detail = arm.baseline_report()
     line = {
         "impl": "reference", "metric": "composited_mblocks_per_s", "value": mbps, "unit": "Mblocks/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int16+fp32", "data": "synthetic",
         "images_per_s": images / total,
-        "config": {"workload": "c3: 1920x1080 4:2:0 q85 JPEG + full-frame tiled alpha logo (48960 blocks/image)",
+        "config": {"workload": WORKLOAD,
                    "sample": f"{threads} images per step (one per host thread)", "inputs": "host-resident decoded coefficients"},
-        "cpu_baseline": {"value": mbps, "unit": "Mblocks/s", "cores": threads, "kind": arm.kind,
-                         "sample": f"{images} x mj_compose (dropon compile + blend) over {threads} threads"},
+        "cpu_baseline": {"value": mbps, "unit": "Mblocks/s", "cores": threads, "kind": arm.kind, "cpu_model": cpu_model(),
+                         "sample": f"{images} x mj_compose (dropon compile + blend) over {threads} threads",
+                         "detail": detail},
         "e2e": {"value": mbps, "unit": "Mblocks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -245,6 +340,68 @@ def run_reference_arm(args, rank: int, world: int):
 # ------------------------------------------------------------------------------------------
 # the B200 arm
 # ------------------------------------------------------------------------------------------
+
+
+def kernel_source_sha() -> str:
+    """fingerprint of the K2 sources: profiles/k2_traffic.json carries the one its ncu capture was taken from"""
+    import hashlib
+
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "libmodjpeg_b200", "csrc")
+    for name in ("k2_compose.cu", "k2_generic_op.cu", "k2_common.cuh", "k2_umma.cuh", "mjx_math.cuh"):
+        with open(os.path.join(d, name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def parity_block(engine, slab, base_flat, jpegs, logo, shapes, plane_bytes, comp_off, lo, k, step, dev) -> dict:
+    """north_star: differing-coefficient count and decoded-pixel PSNR, reported.  The first k images of the resident batch
+    get their pristine planes back, ONE launch of the timed path runs over the whole batch, and those k images are
+    compared with what the unmodified reference (oracle/_ref, the checker) makes of the same inputs."""
+    import io
+
+    import torch
+    from PIL import Image
+
+    from oracle import oracle_py as O
+
+    ref = O.Reference()
+    dref = ref.dropon_from_raw(logo, O.CS_RGBA, 255)
+    for i in range(k):
+        slab[i] = torch.from_numpy(base_flat[(lo + i) % N_BASES]).to(dev)
+    step()
+    torch.cuda.synchronize(dev)
+    got_all = slab[:k].cpu().numpy()
+    n = changed = differ = 0
+    mx = 0
+    psnrs = []
+    for i in range(k):
+        jb = jpegs[(lo + i) % N_BASES]
+        jr = ref.read_jpeg(jb)
+        before = jr.planes()
+        if jr.compose(dref, ALIGN_TOP_LEFT, 0, 0) != 0:
+            raise RuntimeError("reference mj_compose failed")
+        want = jr.planes()
+        jg = ref.read_jpeg(jb)
+        for c, (r, st) in enumerate(shapes):
+            got = got_all[i, int(comp_off[c]):int(comp_off[c]) + plane_bytes[c]].view(np.int16).reshape(r, st, 64)
+            d = got.astype(np.int32) - want[c].astype(np.int32)
+            n += d.size
+            differ += int((d != 0).sum())
+            mx = max(mx, int(np.abs(d).max()))
+            changed += int((want[c] != before[c]).sum())
+            jg.set_plane(c, got)
+        pa = np.asarray(Image.open(io.BytesIO(jg.write(0))), np.float64)
+        pb = np.asarray(Image.open(io.BytesIO(jr.write(0))), np.float64)
+        mse = float(((pa - pb) ** 2).mean())
+        psnrs.append(None if mse == 0 else 10 * np.log10(255.0 ** 2 / mse))
+    finite = [x for x in psnrs if x is not None]
+    return {"images": k, "coefficients": n, "changed_by_compose": changed, "differing_from_reference": differ,
+            "differing_rate_of_changed": differ / max(1, changed), "max_abs_diff_in_quant_steps": mx,
+            "decoded_psnr_db_vs_reference_min": round(min(finite), 2) if finite else "identical",
+            "images_decoding_identically": sum(1 for x in psnrs if x is None),
+            "against": "oracle/_ref = the unmodified reference built here, mj_compose on the same JPEGs",
+            "path": "one launch of the timed kernels over the whole resident batch; the first images compared"}
 
 
 ORIG_AFFINITY = None
@@ -455,6 +612,40 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
         other["k3_effects_pixelate"] = {"ms": ms, "blocks": dc_blocks, "algorithmic_bytes": dc_blocks * 130,
                                         "achieved_gbs": dc_blocks * 130 / (ms * 1e-3) / 1e9, "gblocks_per_s": dc_blocks / (ms * 1e-3) / 1e9}
 
+    # ---- parity of the timed path against the unmodified reference (rank 0, outside every timed region) ----
+    parity = None
+    if rank == 0 and not args.no_parity:
+        try:
+            parity = parity_block(engine, slab, base_flat, jpegs, logo, shapes, plane_bytes, comp_off, lo, min(8, n), step, dev)
+        except Exception as e:  # noqa: BLE001 -- the checker is reported, never required for the GPU number
+            parity = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+
+    # ---- like for like with the reference's mj_compose: dropon compile + blend PER IMAGE, device-resident --------
+    per_image = None
+    if rank == 0 and not args.no_other_kernels:
+        engine.set_stream(stream.cuda_stream)
+        px_d = torch.from_numpy(np.concatenate([i3.reshape(-1), a3.reshape(-1)])).to(dev)
+        npx_d = i3.size
+        k_img = min(n, 64)
+
+        def one_image(i):
+            c = engine.dropon_compile(None, None, M.CS_RGB, layout, (g["blockoffset_x"], g["blockoffset_y"]),
+                                      (g["crop_x"], g["crop_y"], g["crop_w"], g["crop_h"]),
+                                      device_pixels=(px_d.data_ptr(), px_d.data_ptr() + npx_d, logo.shape[1], logo.shape[0]))
+            engine.compose_batch_device(descs_dev.data_ptr() + i * capi.IMAGE_DESC_DTYPE.itemsize, 1, c, g["block_x"], g["block_y"])
+            c.free()
+
+        one_image(0)
+        torch.cuda.synchronize(dev)
+        tp0 = time.perf_counter()
+        for i in range(k_img):
+            one_image(i)
+        torch.cuda.synchronize(dev)
+        tp = time.perf_counter() - tp0
+        per_image = {"value": k_img * blocks_per_image / tp / 1e6, "unit": "Mblocks/s", "images": k_img, "ms_per_image": 1e3 * tp / k_img,
+                     "what": "K1 (mjx_dropon_compile) + K2 on ONE device-resident image per call, nothing reused between images: the work "
+                             "the reference's mj_compose does per call (compile + blend, src/compose.c:155-177), wall clock"}
+
     # ---- e2e: host planes through mjx_compose_batch_host ----------------------------------------
     n_e2e = min(n, args.e2e_images)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -546,8 +737,10 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
             dt = arm.step(reps)
             imgs = threads * reps
             cpu = {"value": imgs * arm.blocks_per_image / dt / 1e6, "unit": "Mblocks/s", "cores": threads, "kind": arm.kind,
+                   "cpu_model": cpu_model(),
                    "sample": f"{imgs} x mj_compose (dropon compile + blend) of the same 1080p images over {threads} host threads",
-                   "images_per_s": imgs / dt}
+                   "images_per_s": imgs / dt,
+                   "detail": arm.baseline_report()}
         except Exception as e:  # the baseline is reported, never required for the GPU number
             cpu = {"value": None, "unit": "Mblocks/s", "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
 
@@ -564,11 +757,14 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
         # per kernel: image bytes by class + the compiled-dropon bytes that class needs, once per launch
         alg_generic = n * counts["G"] * 256 + counts["G"] * (256 + 4)
         alg_simple = n * (counts["OPAQUE"] * 128 + counts["U"] * 256) + (counts["OPAQUE"] + counts["U"]) * (128 + 4)
+        # DRAM bytes per launch from the committed ncu capture -- only while it was taken from these very sources
         traffic = {}
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "k2_traffic.json")))
+            if traffic.get("source_sha") != kernel_source_sha():
+                traffic = {}
         except Exception:
-            pass
+            traffic = {}
         kernels = {
             "k2_generic_kernel": {"class": "G", "launch_ms": ms_generic, "algorithmic_bytes": alg_generic,
                                   "achieved_gbs": alg_generic / (ms_generic * 1e-3) / 1e9 if ms_generic else None,
@@ -586,7 +782,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16+fp32", "data": "synthetic",
             "images_per_s": n_total * args.steps / (total_ms_max * 1e-3),
-            "config": {"workload": "c3: batch of 1920x1080 4:2:0 q85 JPEGs + full-frame tiled alpha logo (BASELINE.json configs[2])",
+            "config": {"workload": WORKLOAD,
                        "images_per_gpu": args.images_per_gpu, "blocks_per_image": blocks_per_image, "class_mix": counts,
                        "resident_bytes_per_gpu": n * image_bytes,
                        "l2": "inputs (7.8 GB/GPU) larger than L2 (126 MB); no flush needed",
@@ -598,6 +794,8 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
                          "step": {"achieved": achieved, "frac": achieved / peak, "algorithmic_bytes": alg_bytes, "ms": launch_ms,
                                   "what": "whole K2 step = k2_generic_kernel with k2_simple_kernel beside it on a side stream (one small CTA per SM fits next to the G kernel's three), joined before the step ends"},
                          "kernels": kernels},
+            "parity": parity,
+            "per_image_compile_and_blend": per_image,
             "other_kernels": other,
             "e2e_files": files,
             "cpu_baseline": cpu,
@@ -632,6 +830,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-kernels", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--file-images", type=int, default=256, help="JPEGs pushed through mj_compose_batch (tier iii); 0 = skip")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

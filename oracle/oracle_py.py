@@ -382,11 +382,12 @@ class Reference(MjLibrary):
         L.mj_compile_dropon.argtypes = [C.POINTER(_CompiledDropon), C.c_void_p, C.c_int, C.POINTER(_Sampling)] + [C.c_int] * 6
         L.mj_free_compileddropon.argtypes = [C.POINTER(_CompiledDropon)]
         L.mj_free_compileddropon.restype = None
+        L.mj_compose_with_mask.argtypes = [C.c_void_p, C.POINTER(_CompiledDropon), C.c_int, C.c_int]
         L.mj_convolve.argtypes = [_f32p, _f32p, C.c_float, C.c_int, C.c_int]
         L.mj_convolve.restype = None
 
-    def compile_dropon(self, d: Dropon, colorspace: int, samp: list[tuple[int, int]], boff_x=0, boff_y=0, crop=None):
-        """mj_compile_dropon (reference: src/dropon.c:325) -> (rv, image[c], alpha[c]) float32 [hb][wb][64]"""
+    def compile_handle(self, d: Dropon, colorspace: int, samp: list[tuple[int, int]], boff_x=0, boff_y=0, crop=None):
+        """mj_compile_dropon (reference: src/dropon.c:325) -> (rv, mj_compileddropon_t); release with free_compiled()"""
         s = _Sampling()
         s.max_h = max(h for h, _ in samp)
         s.max_v = max(v for _, v in samp)
@@ -398,6 +399,18 @@ class Reference(MjLibrary):
         cx, cy, cw, ch = crop if crop is not None else (0, 0, d.width, d.height)
         cd = _CompiledDropon()
         rv = self.lib.mj_compile_dropon(C.byref(cd), d.ptr, colorspace, C.byref(s), boff_x, boff_y, cx, cy, cw, ch)
+        return rv, cd
+
+    def compose_with_mask(self, j: "Jpeg", cd, block_x: int, block_y: int) -> int:
+        """mj_compose_with_mask (reference: src/compose.c:237): the blend alone, on an already compiled dropon"""
+        return self.lib.mj_compose_with_mask(j.ptr, C.byref(cd), block_x, block_y)
+
+    def free_compiled(self, cd) -> None:
+        self.lib.mj_free_compileddropon(C.byref(cd))
+
+    def compile_dropon(self, d: Dropon, colorspace: int, samp: list[tuple[int, int]], boff_x=0, boff_y=0, crop=None):
+        """mj_compile_dropon (reference: src/dropon.c:325) -> (rv, image[c], alpha[c]) float32 [hb][wb][64]"""
+        rv, cd = self.compile_handle(d, colorspace, samp, boff_x, boff_y, crop)
         if rv != 0:
             return rv, None, None
 

@@ -156,6 +156,72 @@ def test_c4_fullframe_generic_vs_oracle(engine, port, gray):
     assert bad <= n * 2e-4
 
 
+@pytest.mark.parametrize("gray", [False, True])
+def test_c4_fullframe_generic_8k_vs_reference(engine, ref, gray):
+    """config 4 (ii) at its stated size: 7680x4320 4:4:4 (1 555 200 blocks) and grayscale (518 400 blocks), full-frame
+    non-uniform alpha -- every block float-blended -- through mj_compose against the unmodified reference (oracle/_ref,
+    ~10 s of CPU per image)"""
+    import libmodjpeg_b200 as M
+
+    W_, H_ = 7680, 4320
+    data = util.jpeg_bytes(W_, H_, "444", 85, seed=4, gray=gray)
+    raw = util.wavy_alpha_rgba(W_, H_)
+    jr = ref.read_jpeg(data)
+    dr = ref.dropon_from_raw(raw, M.CS_RGBA, 255)
+    assert jr.compose(dr, 4 | 1, 0, 0) == 0
+    j = M.Jpeg()
+    assert j.read_jpeg_from_memory(data) == 0
+    ncomp = j.info()["ncomp"]
+    before = j.planes()
+    d = M.Dropon()
+    assert d.read_dropon_from_raw(raw, M.CS_RGBA, 255) == 0
+    assert j.compose(d, 4 | 1, 0, 0) == 0
+    n = bad = changed = 0
+    for c in range(ncomp):
+        got, want = j.plane(c), jr.plane(c)
+        dd = got.astype(np.int32) - want.astype(np.int32)
+        assert np.abs(dd).max() <= 1
+        n += dd.size
+        bad += int((dd != 0).sum())
+        changed += int((want != before[c]).sum())
+    print(f"\nC4 8K {'gray' if gray else '4:4:4'} full-frame generic vs reference: {n} coefficients, {changed} changed, {bad} differ by one step")
+    assert changed > n // 20 and bad <= n * 2e-4
+    jr.free()
+
+
+def test_c5_effects_8k_444_vs_oracle(engine, port):
+    """config 5 on the 8K 4:4:4 image: the four effects through the API, bit-exact"""
+    import libmodjpeg_b200 as M
+
+    data = util.jpeg_bytes(7680, 4320, "444", 85, seed=4)
+    j0 = M.Jpeg()
+    assert j0.read_jpeg_from_memory(data) == 0
+    base = j0.planes()
+    q = [j0.qtable(c) for c in range(3)]
+    ci = [j0.comp_info(c) for c in range(3)]
+    for fx in ("luminance", "tint", "grayscale", "pixelate"):
+        j = M.Jpeg()
+        assert j.read_jpeg_from_memory(data) == 0
+        want = [p.copy() for p in base]
+        if fx == "luminance":
+            assert j.effect_luminance(40) == 0
+            port.effect_add_dc(want[0], ci[0]["wreal"], ci[0]["hreal"], q[0][0], 40)
+        elif fx == "tint":
+            assert j.effect_tint(30, -30) == 0
+            port.effect_add_dc(want[1], ci[1]["wreal"], ci[1]["hreal"], q[1][0], 30)
+            port.effect_add_dc(want[2], ci[2]["wreal"], ci[2]["hreal"], q[2][0], -30)
+        elif fx == "grayscale":
+            assert j.effect_grayscale() == 0
+            for c in (1, 2):
+                port.effect_zero(want[c], ci[c]["wreal"], ci[c]["hreal"])
+        else:
+            assert j.effect_pixelate() == 0
+            for c in range(3):
+                port.effect_pixelate(want[c], ci[c]["wreal"], ci[c]["hreal"])
+        for c, got in enumerate(j.planes()):
+            assert np.array_equal(got, want[c]), (fx, c)
+
+
 @pytest.mark.parametrize("blend", [128, 255])
 def test_c4_fullframe_uniform_alpha_8k_bitexact(engine, port, blend):
     """config 4 (i): 7680x4320 4:4:4, full-frame overlay with one alpha for every pixel -- 1 555 200 blocks of class

@@ -434,7 +434,10 @@ def test_api_compose_golden_c1(engine):
         dd = got[c].astype(np.int32) - G[f"c1_after_{c}"].astype(np.int32)
         assert np.abs(dd).max() <= 1
         nbad += int((dd != 0).sum())
-        assert int((got[c] != before[c]).any(-1).sum()) == int(G[f"c1_changed_blocks_{c}"]) or nbad
+        # the count of changed blocks is the golden one; only a block holding one of the (at most 3) one-step
+        # differences may flip between changed and unchanged
+        off_blocks = int((dd != 0).any(-1).sum())
+        assert abs(int((got[c] != before[c]).any(-1).sum()) - int(G[f"c1_changed_blocks_{c}"])) <= off_blocks
     assert nbad <= 3
     # alpha of dropon.png is {0, 64, 255}: every block away from the glyph edges is T, U or OPAQUE -> mostly exact
     rv, out = j.write_jpeg_to_memory(0)
