@@ -117,8 +117,9 @@ int         mjx_ctx_set_strict(mjx_ctx *ctx, int strict);
  * Env MJX_K2_TC sets the initial mode.  The cache (16 or 24 KB per class G block, MJX_K2_OP_MAX_MB caps it, default 4096)
  * belongs to the first ctx that uses the dropon this way; other ctxs run the fp32 kernel with it. */
 int         mjx_ctx_set_tensor_core(mjx_ctx *ctx, int mode);
-/* fp16 pieces per operator entry: 2 (default, 22 significant bits) or 3 (33 bits); takes effect for dropons whose cache
- * has not been allocated yet.  Env MJX_K2_OP_PIECES sets the initial value. */
+/* fp16 pieces per operator entry: 2 (22 significant bits) is the only value the kernel is built for -- it reproduces the
+ * reference on every test image (tests/test_gpu_tensor_core.py); the call exists so that a build with more pieces stays
+ * source compatible. */
 int         mjx_ctx_set_operator_pieces(mjx_ctx *ctx, int pieces);
 /* on = 1 (default): mjx_compose_batch_host runs K2 directly on page-locked (GPU-addressable) host planes, so only
  * the blocks the dropon touches cross PCIe; 0: always stage the region under the dropon through device memory */

@@ -19,13 +19,13 @@ struct FastParams {
 };
 
 // ---- the tensor-core G kernel of large batches (k2_generic_op.cu) ---------------------------------------------------
-static constexpr int kOpGroups = 4; // groups of four warps per CTA, one 128-image UMMA in flight each
+static constexpr int kOpGroups = 3; // groups of four compute warps per CTA (three shared-memory stages and two accumulators each)
 
 // device pointers into the operator cache of a compiled dropon
 struct OpView {
     unsigned char *B;       // [n_generic][np][8192] operator pieces, fp16, stored as SWIZZLE_128B shared-memory images
     float         *K;       // [n_generic][64] L(D): the overlay's share of the blend term
-    unsigned char *diag;    // [MJX_MAX_COMPONENTS][8192] diag(q) half of the first piece's tile
+    float         *q512;    // [MJX_MAX_COMPONENTS][64] 512 q (the staged fp16 operand is I / 512)
     float         *rq;      // [MJX_MAX_COMPONENTS][64] biased reciprocals of the tables
     uint16_t      *key;     // [MJX_MAX_COMPONENTS][64] the tables the cache was built for
     int           *info;    // [MJX_MAX_COMPONENTS] log2 of the operator's scale, -1: component not served (q > 255)
@@ -71,6 +71,12 @@ __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)_
 // 16 bytes global -> shared; nbytes == 0 zero-fills without touching `src` (no branch for absent blocks)
 __device__ __forceinline__ void cp_async16(unsigned dst, const void *src, unsigned nbytes = 16u) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+}
+// the same past L1 (L2 only): a streaming gather must not depend on L1 lines for its misses in flight -- with 227 KB of the SM's
+// 256 KB given to shared memory the L1 that is left holds ~200 lines, which caps the bytes in flight per SM (measured:
+// k2_generic_op_kernel's gather alone 1.88 ms with .ca)
+__device__ __forceinline__ void cp_async16_cg(unsigned dst, const void *src, unsigned nbytes = 16u) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>

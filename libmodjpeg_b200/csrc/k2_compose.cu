@@ -37,6 +37,8 @@
 //
 // Roofline: HBM.  Algorithmic bytes per block: T 0, OPAQUE 128 (write), U/G 256 (read + write),
 // plus the compiled dropon once per launch (L2 / shared-memory resident across the images).
+#include <stdlib.h>
+
 #include "k2_common.cuh"
 
 namespace mjx {

@@ -48,6 +48,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
     __trap();
 }
+// busy-polling wait (test_wait never suspends the thread): lowest wake-up latency, for warps that have nothing else to do
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+    for(int spin = 0; spin < (1 << 26); spin++) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if(ok) return;
+    }
+    __trap();
+}
+// has the phase with this parity completed?  (does not block)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 // contiguous global -> shared copy by the bulk-copy engine (16-byte aligned, size a multiple of 16); completion is
 // signalled to the mbarrier as `bytes` of its expected transaction count
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -75,6 +90,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
                    "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
                  : "r"(taddr)
                  : "memory");
+}
+// 16 lanes x 64 consecutive fp32 columns in the fragment layout of mma: thread t receives, for j = 0..7,
+//   v[4j + 0..1] = lane (t >> 2),     columns 8j + 2 (t & 3) + {0, 1}
+//   v[4j + 2..3] = lane (t >> 2) + 8, the same columns
+// i.e. a fixed set of 16 columns per thread, whatever the lane
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, float *v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+        "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]),
+          "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]), "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]),
+          "=f"(v[23]), "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+        : "r"(taddr)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

@@ -107,7 +107,6 @@ int mjx_ctx_create(mjx_ctx **out, int device) {
     ctx->stream = ctx->own_stream;
     if(const char *ev = getenv("MJX_K2_OVERLAP")) ctx->overlap = atoi(ev) != 0;
     if(const char *ev = getenv("MJX_K2_TC")) ctx->k2_tc = atoi(ev) < 0 ? 0 : (atoi(ev) > 2 ? 2 : atoi(ev));
-    if(const char *ev = getenv("MJX_K2_OP_PIECES")) ctx->k2_op_pieces = atoi(ev) >= 3 ? 3 : 2;
     if(const char *ev = getenv("MJX_K2_OP_MAX_MB")) ctx->k2_op_max_bytes = (size_t)(atoll(ev) > 0 ? atoll(ev) : 0) << 20;
     *out = ctx;
     return MJX_OK;
@@ -599,7 +598,7 @@ int mjx_ctx_set_tensor_core(mjx_ctx *ctx, int mode) {
 }
 
 int mjx_ctx_set_operator_pieces(mjx_ctx *ctx, int pieces) {
-    if(!ctx || (pieces != 2 && pieces != 3)) return MJX_ERR_ARG;
+    if(!ctx || pieces != 2) return MJX_ERR_ARG; // the kernel's shared-memory budget holds two pieces per operator
     ctx->k2_op_pieces = pieces;
     return MJX_OK;
 }
