@@ -172,6 +172,17 @@ typedef struct {
 int mj_compose_batch(int n, const mj_blob_t *in, mj_blob_t *out, int *status, mj_dropon_t *d, unsigned int align, int offset_x,
                      int offset_y, int write_options, int nthreads);
 
+/* ---- additive: request coalescer (not in the reference) ---------------------------------
+ * For request servers (the nginx filter's shape: many threads, one image per call, one shared logo).  When enabled,
+ * concurrent mj_compose calls with the same dropon, target layout and placement remainder are gathered -- for at most
+ * `wait_us` microseconds or `max_batch` requests -- into ONE kernel launch over a shared page-locked slab, and the
+ * dropon is compiled once per key instead of once per call.  Results are byte-identical to unbatched calls; a call
+ * still returns only when its image holds the result.  Off by default (it adds up to wait_us of latency to a lone
+ * request); MJX_COALESCE=1 [MJX_COALESCE_MAX, MJX_COALESCE_WAIT_US] in the environment switches it on without code.
+ * max_batch <= 0 / wait_us < 0 keep the current values (defaults 32 and 200). */
+void mj_coalesce_configure(int enable, int max_batch, int wait_us);
+void mj_coalesce_stats(unsigned long *batches, unsigned long *requests); /* launches made / requests served so far */
+
 #ifdef __cplusplus
 }
 #endif

@@ -445,6 +445,10 @@ def load_modjpeg() -> C.CDLL:
     L.mjx_jpeg_export_plane.argtypes = [vp, C.c_int, vp]
     L.mjx_jpeg_import_plane.argtypes = [vp, C.c_int, vp]
     L.mjx_jpeg_layout.argtypes = [vp, C.POINTER(Layout)]
+    L.mj_coalesce_configure.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.mj_coalesce_configure.restype = None
+    L.mj_coalesce_stats.argtypes = [C.POINTER(C.c_ulong), C.POINTER(C.c_ulong)]
+    L.mj_coalesce_stats.restype = None
     L.mj_compose_batch.argtypes = [C.c_int, C.POINTER(Blob), C.POINTER(Blob), C.POINTER(C.c_int), vp, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int]
     L.mjx_host_ctx.argtypes = []
     L.mjx_host_ctx.restype = vp
@@ -560,6 +564,18 @@ class Jpeg:
 class Blob(C.Structure):
     """mj_blob_t (include/libmodjpeg.h)"""
     _fields_ = [("data", C.c_void_p), ("len", C.c_size_t)]
+
+
+def coalesce_configure(enable: bool, max_batch: int = 0, wait_us: int = -1) -> None:
+    """request coalescer of mj_compose (libmodjpeg_b200/csrc/host/mj_coalesce.c): concurrent calls with one dropon share a launch"""
+    load_modjpeg().mj_coalesce_configure(1 if enable else 0, max_batch, wait_us)
+
+
+def coalesce_stats() -> tuple[int, int]:
+    """(launches made, requests served) by the coalescer so far"""
+    b, r = C.c_ulong(0), C.c_ulong(0)
+    load_modjpeg().mj_coalesce_stats(C.byref(b), C.byref(r))
+    return b.value, r.value
 
 
 def compose_batch(jpegs: list[bytes], dropon: "Dropon", align: int, offset_x: int = 0, offset_y: int = 0, options: int = 0,

@@ -105,6 +105,11 @@ int mj_compose(mj_jpeg_t *m, mj_dropon_t *d, unsigned int align, int offset_x, i
     mjx_ctx *ctx = mjx_host_ctx();
     if(ctx == NULL) return MJ_ERR_DEVICE;
 
+    if(mjp_coalesce_enabled()) { /* opt-in: concurrent calls with the same dropon share one launch (mj_coalesce.c) */
+        int result = MJ_OK;
+        if(mjp_coalesce_compose(m, d, &layout, &g, &result)) return result;
+    }
+
     mjx_dropon *cd = NULL;
     int         cd_owned = 1;
     rv = get_compiled(ctx, d, &layout, &g, &cd, &cd_owned);

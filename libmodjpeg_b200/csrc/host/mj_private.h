@@ -59,6 +59,11 @@ int mjp_read_whole_file(unsigned char **buffer, size_t *len, const char *filenam
 /* frees the calling thread's cached compiled dropons (mj_compose.c, MJX_DROPON_CACHE=1) */
 void mjp_compose_cache_clear(void);
 
+/* request coalescer (mj_coalesce.c): 1 when mj_compose should try it; mjp_coalesce_compose returns 1 when it served the
+ * request (*result = mj_compose's return value), 0 when the ordinary path has to */
+int mjp_coalesce_enabled(void);
+int mjp_coalesce_compose(mj_jpeg_t *m, mj_dropon_t *d, const mjx_layout_t *layout, const mjx_geometry_t *g, int *result);
+
 /* MJX_* -> MJ_* */
 int mjp_map_error(int mjx_rv);
 

@@ -205,7 +205,9 @@ __global__ void __launch_bounds__(256) k2_op_build_kernel(const OpParams p) {
         for(int l = 0; l < 8; l++)
 #pragma unroll
             for(int a = 0; a < 8; a++) k += s_u[l][m][a] * s_p[l][n][a];
-        p.op.K[(size_t)slot * 64 + t] = (float)k;
+        // stored in the order the kernel's threads read it: a thread of class q4 = lane & 3 owns coefficients 8 j + 2 q4 + e
+        // (j = 0..7, e = 0, 1) -- its 16 values lie together: position 16 q4 + 2 j + e
+        p.op.K[(size_t)slot * 64 + 16 * ((t & 7) >> 1) + 2 * (t >> 3) + (t & 1)] = (float)k;
     }
     // the component's first slot also writes what depends on the tables only: 1/q (biased) and 512 q
     if(slot == p.drop.gtile_start[c] * 32 && t < 64) {
@@ -261,6 +263,11 @@ struct OpSmem {
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
     return v;
 }
 __device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
@@ -371,6 +378,7 @@ __global__ void __launch_bounds__(kOpThreads, 1) k2_generic_op_kernel(const OpPa
                 const uint64_t bd0 = umma_desc_sw128(base32 + L::kB + buf * L::kBBuf);
                 for(int k = 0; k < bpg; k++, u++) {
                     const int st = u % kOpStages, acc = u & 1;
+                    // (busy polling: a suspended wait wakes this lane too late -- 1.51 instead of 1.46 ms on the bench batch)
                     mbar_spin(bar(OpBars::kConv + g * kOpStages + st), (u / kOpStages) & 1);
                     if(u >= 2) mbar_spin(bar(OpBars::kFree + g * 2 + acc), ((u >> 1) - 1) & 1);
                     tc_fence_after();
@@ -516,16 +524,19 @@ __global__ void __launch_bounds__(kOpThreads, 1) k2_generic_op_kernel(const OpPa
                     __syncwarp();
                     // ---- int16 -> fp16 (I / 512) in place, thread per row ----
                     const uint32_t my_row = my_row0 + st * kOpStageBytes;
-                    uint32_t       viol = 0;
+                    uint32_t       vmax = 0x80008000u, vmin = 0x7fff7fffu; // running max / min of the row's coefficients, two int16 lanes
                     uint4          w[8];
 #pragma unroll
                     for(int ch = 0; ch < 8; ch++) w[ch] = lds128(my_row + ((ch ^ rsw) << 4));
 #pragma unroll
                     for(int ch = 0; ch < 8; ch++) {
                         uint32_t *pw = &w[ch].x;
+                        if(kCheck) { // one packed three-input max and one min per two words (VIMNMX3.S16x2)
+                            vmax = __vimax3_s16x2(vmax, pw[0], pw[1]), vmax = __vimax3_s16x2(vmax, pw[2], pw[3]);
+                            vmin = __vimin3_s16x2(vmin, pw[0], pw[1]), vmin = __vimin3_s16x2(vmin, pw[2], pw[3]);
+                        }
 #pragma unroll
                         for(int i = 0; i < 4; i++) {
-                            if(kCheck) viol |= pw[i] ^ (pw[i] << 1); // bits 15..10 of each half all equal <=> in [-1024, 1023]
                             uint32_t x;
                             asm("lop3.b32 %0, %1, 0x07FF07FF, %2, 0x6A;" : "=r"(x) : "r"(pw[i]), "r"(kx)); // (w & mask) ^ kx
                             asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(pw[i]) : "r"(x), "r"(0x78007800u), "r"(0xC000C000u));
@@ -534,7 +545,8 @@ __global__ void __launch_bounds__(kOpThreads, 1) k2_generic_op_kernel(const OpPa
                     }
                     if(kCheck) {
                         const uint32_t ad = waddr + st * 256 + lane * 8;
-                        if((viol & 0xF800F800u) != 0 && lds64(ad) != 0ull) { // leave this block to the fp32 kernel: one bit per (list slot, image), and do not store it
+                        const int      hi = max((int)(int16_t)(vmax & 0xffffu), (int)vmax >> 16), lo = min((int)(int16_t)(vmin & 0xffffu), (int)vmin >> 16);
+                        if((hi > 1023 || lo < -1024) && lds64(ad) != 0ull) { // leave this block to the fp32 kernel: one bit per (list slot, image), and do not store it
                             const int slot = 2 * (blockIdx.x + pc.j * gridDim.x) + half;
                             atomicOr(p.redo_mask + (size_t)(slot >> 5) * p.n + image_of(pc), 1u << (slot & 31));
                             atomicAdd(p.redo_count, 1u);
@@ -563,7 +575,7 @@ __global__ void __launch_bounds__(kOpThreads, 1) k2_generic_op_kernel(const OpPa
                     }
                     mbar_wait(bar(OpBars::kMma + grp * 2 + acc), (v >> 1) & 1); // (also: the item's K have landed)
                     tc_fence_after();
-                    const uint32_t sK = base32 + L::kK + (pe.jv & (kOpKRing - 1)) * 512 + 2 * q4 * 4;
+                    const uint32_t sK = base32 + L::kK + (pe.jv & (kOpKRing - 1)) * 512 + q4 * 64;
                     // word (q4) of chunk j of tile row 64 h + 16 wq + r8 + 8 s2: the fp16 pair I / 512 on the way in, the int16 pair on
                     // the way out; lanes 16 h .. 16 h + 15 of the quarter hold half h
                     const uint32_t my_w = stage0 + st * kOpStageBytes + (16 * wq + r8) * 128 + q4 * 4;
@@ -571,9 +583,12 @@ __global__ void __launch_bounds__(kOpThreads, 1) k2_generic_op_kernel(const OpPa
                     for(int h = 0; h < 2; h++) {
                         float y[32];
                         tmem_ld_16x256b_x8(taddr + ((uint32_t)(16 * h) << 16) + acc * 64, y);
-                        F2 k2[8]; // K of the slot this half belongs to
+                        F2 k2[8]; // K of the slot this half belongs to (stored per thread class: 64 contiguous bytes)
 #pragma unroll
-                        for(int j = 0; j < 8; j++) k2[j] = lds64f(sK + h * 256 + j * 32);
+                        for(int j4 = 0; j4 < 4; j4++) {
+                            const float4 kk = lds128f(sK + h * 256 + j4 * 16);
+                            k2[2 * j4] = f2(kk.x, kk.y), k2[2 * j4 + 1] = f2(kk.z, kk.w);
+                        }
                         tmem_wait_ld();
                         if(h == 1) {
                             tc_fence_before();

@@ -44,61 +44,72 @@ __device__ __forceinline__ int fold_dc(const K3Params &p, int dc, int q0) {
 }
 
 static constexpr int kThreads = 256;
+static constexpr int kDcUnroll = 8; // independent DC loads in flight per thread
 
-// component ends with AC == 0: 8 lanes per block, every lane stores its (zero) row; a CTA owns whole block rows
+// Component ends with AC == 0 ("rewrite": pixelate, grayscale).  A warp owns runs of 32 consecutive blocks of one block row
+// (4 KB); the two halves of the job are decoupled so that neither waits for the other:
+//   gather:  lane i fetches the DC of block i (one 2-byte load = one DRAM sector per block), kDcUnroll runs deep, so a
+//            warp has 32 x kDcUnroll sectors in flight before it stores anything;
+//   stream:  8 lanes per block write its 128 bytes (the folded DC in the first word, zeros elsewhere) with 128-bit streaming
+//            stores, four blocks per instruction; the lane that writes a block's first chunk gets the DC by shuffle.
+// Work item = (block row, group of kDcUnroll runs) of image blockIdx.y, dealt to the warps of the image's CTAs.
 __global__ void __launch_bounds__(kThreads) k3_rewrite_kernel(const K3Params p, int first_is_zero) {
+    const int lane = threadIdx.x & 31;
+    const int c = p.comp;
     const mjx_image_desc_t &im = p.items[blockIdx.y];
-    const int c = p.comp, r = threadIdx.x & 7;
-    const int wreal = im.wreal[c], hreal = im.hreal[c], stride = im.stride_blocks[c];
+    const int wreal = im.wreal[c], hreal = im.hreal[c];
+    if(im.plane[c] == 0 || wreal <= 0) return;
     const int q0 = im.q[c][0];
-    int16_t  *plane = reinterpret_cast<int16_t *>(im.plane[c]);
-    for(int l = blockIdx.x; l < hreal; l += gridDim.x) {
-        int16_t *rowp = plane + (size_t)l * stride * 64;
-        // four blocks per thread and trip: the DC loads of all four are in flight before the first store
-        for(int k0 = threadIdx.x >> 3; k0 < wreal; k0 += 4 * (kThreads / 8)) {
-            int dc[4] = {0, 0, 0, 0};
-            if(r == 0 && !first_is_zero) {
+    const int groups = (wreal + 32 * kDcUnroll - 1) / (32 * kDcUnroll); // per block row
+    const int items = hreal * groups, warps = gridDim.x * (kThreads / 32);
+    for(int it = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); it < items; it += warps) {
+        const int l = it / groups, g = it - l * groups;
+        int16_t  *rowp = reinterpret_cast<int16_t *>(im.plane[c]) + (size_t)l * im.stride_blocks[c] * 64;
+        const int k_base = g * kDcUnroll * 32;
+        int dc[kDcUnroll];
 #pragma unroll
-                for(int u = 0; u < 4; u++) {
-                    const int k = k0 + u * (kThreads / 8);
-                    if(k < wreal) dc[u] = p.dc_compact ? (int)p.dc_compact[(size_t)l * wreal + k] : (int)rowp[(size_t)k * 64];
-                }
-            }
+        for(int u = 0; u < kDcUnroll; u++) {
+            const int k = k_base + u * 32 + lane;
+            dc[u] = 0;
+            if(!first_is_zero && k < wreal) dc[u] = p.dc_compact ? (int)p.dc_compact[(size_t)l * wreal + k] : (int)__ldcs(rowp + (size_t)k * 64);
+        }
 #pragma unroll
-            for(int u = 0; u < 4; u++) {
-                const int k = k0 + u * (kThreads / 8);
-                if(k >= wreal) break;
-                Row8 row;
-                row.w[0] = row.w[1] = row.w[2] = row.w[3] = 0;
-                if(r == 0) row.w[0] = (uint32_t)fold_dc(p, dc[u], q0) & 0xffffu;
-                st_row_stream(rowp + (size_t)k * 64 + r * 8, row);
+        for(int u = 0; u < kDcUnroll; u++) {
+            const int k0 = k_base + u * 32;
+            if(k0 >= wreal) break; // warp-uniform
+            const int folded = fold_dc(p, dc[u], q0) & 0xffff;
+            int16_t  *runp = rowp + (size_t)k0 * 64 + lane * 8; // lane -> 16-byte chunk (lane & 7) of block (lane >> 3) + 4 i
+#pragma unroll
+            for(int i = 0; i < 8; i++) {
+                const int blk = 4 * i + (lane >> 3);
+                const int v = __shfl_sync(0xffffffffu, folded, blk);
+                if(k0 + blk < wreal) __stcs(reinterpret_cast<uint4 *>(runp + (size_t)i * 256), make_uint4((lane & 7) == 0 ? (uint32_t)v : 0u, 0u, 0u, 0u));
             }
         }
     }
 }
 
-// DC-only pipeline: one thread per block.  A CTA owns block rows l = blockIdx.x, blockIdx.x + gridDim.x, ..;
-// its threads walk the columns, four rows at a time so that four independent 2-byte loads are in flight per
-// thread (the pass moves one 32-byte DRAM sector each way per 128-byte block: it lives on memory parallelism).
+// DC-only pipeline (tint, luminance): one thread per block, kDcUnroll consecutive block ROWS per thread so that its loads are
+// independent and all in flight before the first store.  The pass moves one 32-byte DRAM sector each way per 128-byte block: it
+// lives on memory parallelism.  Work item = (group of kDcUnroll block rows, 256 columns) of image blockIdx.y.
 __global__ void __launch_bounds__(kThreads) k3_dc_kernel(const K3Params p) {
-    const mjx_image_desc_t &im = p.items[blockIdx.y];
     const int c = p.comp;
+    const mjx_image_desc_t &im = p.items[blockIdx.y];
     const int wreal = im.wreal[c], hreal = im.hreal[c], stride = im.stride_blocks[c];
+    if(im.plane[c] == 0 || wreal <= 0) return;
     const int q0 = im.q[c][0];
-    int16_t  *plane = reinterpret_cast<int16_t *>(im.plane[c]);
-    for(int l0 = blockIdx.x * 4; l0 < hreal; l0 += gridDim.x * 4) {
-        for(int k = threadIdx.x; k < wreal; k += kThreads) {
-            int16_t *bp[4];
-            int      dc[4];
+    const int rgroups = (hreal + kDcUnroll - 1) / kDcUnroll, cgroups = (wreal + kThreads - 1) / kThreads;
+    for(int it = blockIdx.x; it < rgroups * cgroups; it += gridDim.x) {
+        const int rg = it / cgroups, cg = it - rg * cgroups;
+        const int k = cg * kThreads + threadIdx.x, l0 = rg * kDcUnroll;
+        if(k >= wreal) continue;
+        int16_t  *bp = reinterpret_cast<int16_t *>(im.plane[c]) + ((size_t)l0 * stride + k) * 64;
+        int       dc[kDcUnroll];
 #pragma unroll
-            for(int u = 0; u < 4; u++) {
-                bp[u] = plane + ((size_t)(l0 + u) * stride + k) * 64;
-                dc[u] = (l0 + u < hreal) ? (int)*bp[u] : 0;
-            }
+        for(int u = 0; u < kDcUnroll; u++) dc[u] = (l0 + u < hreal) ? (int)bp[(size_t)u * stride * 64] : 0;
 #pragma unroll
-            for(int u = 0; u < 4; u++)
-                if(l0 + u < hreal) *bp[u] = (int16_t)fold_dc(p, dc[u], q0);
-        }
+        for(int u = 0; u < kDcUnroll; u++)
+            if(l0 + u < hreal) bp[(size_t)u * stride * 64] = (int16_t)fold_dc(p, dc[u], q0);
     }
 }
 
@@ -143,10 +154,10 @@ cudaError_t launch_k3(cudaStream_t s, const mjx_image_desc_t *items_dev, int n, 
             if(ops[i].op == MJX_FX_ZERO || ops[i].op == MJX_FX_PIXELATE) rewrite = true;
         }
         if(p.nops == 0) continue;
-        // CTAs per image: enough for 148 SMs x 8 resident CTAs a few times over; each CTA strides over block rows
+        // CTAs per image: enough to fill 148 SMs x 8 resident CTAs a few times over; each CTA strides over the image's work items
         int gx = (148 * 32 + n - 1) / n;
         if(gx < 1) gx = 1;
-        if(gx > 1024) gx = 1024;
+        if(gx > 512) gx = 512;
         for(int first = 0; first < n; first += 65535) {
             const int cnt = n - first < 65535 ? n - first : 65535;
             p.items = items_dev + first;

@@ -105,6 +105,10 @@ int mjx_ctx_create(mjx_ctx **out, int device) {
         return MJX_ERR_DEVICE;
     }
     ctx->stream = ctx->own_stream;
+    if(const char *ev = getenv("MJX_L2_FETCH")) { // experiment: L2 fill granularity hint (32 / 64 / 128 bytes), device-wide
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(ev));
+        cudaGetLastError();
+    }
     if(const char *ev = getenv("MJX_K2_OVERLAP")) ctx->overlap = atoi(ev) != 0;
     if(const char *ev = getenv("MJX_K2_TC")) ctx->k2_tc = atoi(ev) < 0 ? 0 : (atoi(ev) > 2 ? 2 : atoi(ev));
     if(const char *ev = getenv("MJX_K2_OP_MAX_MB")) ctx->k2_op_max_bytes = (size_t)(atoll(ev) > 0 ? atoll(ev) : 0) << 20;

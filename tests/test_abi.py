@@ -28,14 +28,15 @@ def test_libmodjpeg_exports_reference_api(built):
     C.CDLL(built["libmjx"], mode=C.RTLD_GLOBAL)
     lib = C.CDLL(built["libmodjpeg"])
     names = _declared("libmodjpeg.h", "mj_")
-    # the reference's 16 public functions (reference: src/libmodjpeg.h:129-149) + the additive batch pipeline
-    assert "mj_compose_batch" in names
-    names = [n for n in names if n != "mj_compose_batch"]
+    # the reference's 16 public functions (reference: src/libmodjpeg.h:129-149) + the additive batch pipeline and coalescer
+    additive = ["mj_compose_batch", "mj_coalesce_configure", "mj_coalesce_stats"]
+    assert all(a in names for a in additive)
+    names = [n for n in names if n not in additive]
     assert names == sorted(["mj_init_dropon", "mj_read_dropon_from_raw", "mj_read_dropon_from_memory", "mj_read_dropon_from_file",
                             "mj_init_jpeg", "mj_read_jpeg_from_memory", "mj_read_jpeg_from_file", "mj_compose",
                             "mj_write_jpeg_to_memory", "mj_write_jpeg_to_file", "mj_free_jpeg", "mj_free_dropon",
                             "mj_effect_grayscale", "mj_effect_pixelate", "mj_effect_tint", "mj_effect_luminance"])
-    for n in names + ["mj_compose_batch"] + _declared("mjx_host.h", "mjx_"):
+    for n in names + additive + _declared("mjx_host.h", "mjx_"):
         assert hasattr(lib, n), n
 
 

@@ -650,6 +650,51 @@ def test_api_threads_are_independent(engine):
             assert np.array_equal(a, b)
 
 
+def test_coalesced_compose_equals_unbatched(engine):
+    """request coalescer: 8 threads composing different images with ONE dropon, at two placements and on
+    two image sizes (different keys must not share a batch) -- byte-identical to the unbatched calls, fewer launches than
+    requests"""
+    import threading
+
+    import libmodjpeg_b200 as M
+    from libmodjpeg_b200 import capi
+
+    datas = [util.jpeg_bytes(320, 240, "420", 85, seed=60 + i) for i in range(6)] + [util.jpeg_bytes(208, 144, "420", 85, seed=70 + i) for i in range(2)]
+    raw = util.logo_rgba(160, 120, 32, 13)
+    d = M.Dropon()
+    assert d.read_dropon_from_raw(raw, M.CS_RGBA, 255) == 0
+    jobs = [(i, datas[i % len(datas)], (M.ALIGN_CENTER, 0, 0) if i % 3 else (M.ALIGN_TOP | M.ALIGN_LEFT, 8, 16)) for i in range(48)]
+
+    def run_all(nthreads):
+        out = [None] * len(jobs)
+
+        def work(t):
+            for i, data, (al, ox, oy) in jobs[t::nthreads]:
+                j = M.Jpeg()
+                assert j.read_jpeg_from_memory(data) == 0
+                assert j.compose(d, al, ox, oy) == 0
+                out[i] = [p.copy() for p in j.planes()]
+
+        ts = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        return out
+
+    plain = run_all(8)
+    b0, r0 = capi.coalesce_stats()
+    capi.coalesce_configure(True, 8, 3000)
+    try:
+        merged = run_all(8)
+    finally:
+        capi.coalesce_configure(False)
+    b1, r1 = capi.coalesce_stats()
+    assert r1 - r0 == len(jobs) and 0 < b1 - b0 < len(jobs), (b1 - b0, r1 - r0)
+    for a, b in zip(plain, merged):
+        for pa, pb in zip(a, b):
+            assert np.array_equal(pa, pb)
+    print(f"\ncoalescer: {r1 - r0} requests in {b1 - b0} launches")
+
+
 def test_k2_strict_mode_reproduces_int16_wraparound(engine, port):
     """adversarial coefficients (|I*q| far outside int16): the strict kernel follows the reference's
     wrap-around bit for bit on T/U/OPAQUE blocks and to +-1 step on G blocks."""
