@@ -671,7 +671,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
 
     def e2e_run(zero_copy: bool):
         engine.set_zero_copy(zero_copy)
-        engine.compose_batch_host(items, min(n_e2e, 8), cd, g["block_x"], g["block_y"])  # warm the staging pools
+        engine.compose_batch_host(items, n_e2e, cd, g["block_x"], g["block_y"])  # untimed: staging pools, first touch of the page-locked planes
         barrier()
         l0 = engine.kernel_launches
         te0 = time.perf_counter()
@@ -696,26 +696,52 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
     roi_bytes = sum(cd.dims(c)[0] * cd.dims(c)[1] * 128 for c in range(3))
     engine.host_free(pinned)
 
-    # ---- tier (iii): JPEG bytes in -> JPEG bytes out through mj_compose_batch (rank 0, N = 1 only) ------
+    # ---- what bounds the e2e tier when several ranks stream host memory at once: the host's own copy bandwidth --------
+    host_copy = None
+    try:
+        nb_copy = 256 << 20
+        src, dst = np.ones(nb_copy, np.uint8), np.empty(nb_copy, np.uint8)
+        np.copyto(dst, src)
+        barrier()
+        th0 = time.perf_counter()
+        for _ in range(4):
+            np.copyto(dst, src)
+        th = time.perf_counter() - th0
+        tt = torch.tensor([th], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        host_copy = {"gbs_all_ranks": world * 4 * 2 * nb_copy / float(tt.item()) / 1e9, "ranks": world,
+                     "what": "every rank copies 256 MB host -> host four times at the same moment (one thread each, bytes read + written): "
+                             "the host DRAM the PCIe streams of all ranks share"}
+        del src, dst
+    except Exception as e:  # noqa: BLE001
+        host_copy = {"unavailable": str(e)[:120]}
+
+    # ---- tier (iii): JPEG bytes in -> JPEG bytes out through mj_compose_batch, every rank its share of host threads -------
     files = None
-    if rank == 0 and world == 1 and args.file_images > 0:
+    if args.file_images > 0:
         if ORIG_AFFINITY:
             os.sched_setaffinity(0, ORIG_AFFINITY)  # entropy coding uses every host core, for both arms
-        threads = host_threads()
+        threads = max(1, host_threads() // world)
         d = M.Dropon()
         assert d.read_dropon_from_raw(logo, M.CS_RGBA, 255) == 0
         batch = [jpegs[i % len(jpegs)] for i in range(args.file_images)]
         capi.compose_batch(batch[:4 * threads], d, ALIGN_TOP_LEFT, 0, 0, 0, nthreads=threads)  # warm the page-locked slab (one full window)
+        barrier()
         tm = {}
         rvb, status, outs = capi.compose_batch(batch, d, ALIGN_TOP_LEFT, 0, 0, 0, nthreads=threads, timing=tm)
-        tf = tm["call_s"]  # wall time of the C call (JPEG bytes in -> malloc()ed JPEG bytes out)
         assert rvb == 0 and not any(status), (rvb, status[:8])
-        files = {"images": args.file_images, "threads": threads, "images_per_s": args.file_images / tf,
-                 "mblocks_per_s": args.file_images * blocks_per_image / tf / 1e6,
-                 "path": "mj_compose_batch: libjpeg entropy decode (thread pool) -> K1 once -> K2 one launch per window, zero-copy "
-                         "on a page-locked slab -> libjpeg entropy encode (thread pool); JPEG bytes in, JPEG bytes out",
-                 "bytes_in": sum(len(b) for b in batch), "bytes_out": sum(len(o) for o in outs)}
-        if not args.no_cpu_baseline:
+        tfm = torch.tensor([tm["call_s"]], dtype=torch.float64, device=dev)  # wall time of the C call (JPEG bytes in -> malloc()ed JPEG bytes out)
+        if dist is not None:
+            dist.all_reduce(tfm, op=dist.ReduceOp.MAX)
+        tf = float(tfm.item())
+        if rank == 0:
+            files = {"images": args.file_images * world, "threads_per_rank": threads, "ranks": world, "images_per_s": args.file_images * world / tf,
+                     "mblocks_per_s": args.file_images * world * blocks_per_image / tf / 1e6,
+                     "path": "mj_compose_batch per rank: libjpeg entropy decode (thread pool) -> K1 once -> K2 one launch per window, zero-copy "
+                             "on a page-locked slab -> libjpeg entropy encode (thread pool); JPEG bytes in, JPEG bytes out",
+                     "bytes_in": sum(len(b) for b in batch) * world, "bytes_out": sum(len(o) for o in outs) * world}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
             try:
                 nref = max(threads, min(args.file_images, 2 * threads))
                 dtr = reference_file_pipeline(jpegs, logo, threads, nref)
@@ -765,16 +791,20 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
                 traffic = {}
         except Exception:
             traffic = {}
+        g_name = "k2_generic_op_kernel" if engine.tensor_core_active(n, counts["G"]) else "k2_generic_kernel"
         kernels = {
-            "k2_generic_kernel": {"class": "G", "launch_ms": ms_generic, "algorithmic_bytes": alg_generic,
+            g_name: {"class": "G", "launch_ms": ms_generic, "algorithmic_bytes": alg_generic,
                                   "achieved_gbs": alg_generic / (ms_generic * 1e-3) / 1e9 if ms_generic else None,
-                                  "traffic": traffic.get("k2_generic_kernel")},
+                                  "traffic": traffic.get(g_name),
+                                  "path": ("tensor-core operator kernel (tcgen05, fp16 operands / fp32 accumulation; libmodjpeg_b200/csrc/k2_generic_op.cu) + "
+                                           "its prepare / cache-check / redo launches; coefficient range checked in the kernel"
+                                           if g_name == "k2_generic_op_kernel" else "fp32 kernel (libmodjpeg_b200/csrc/k2_compose.cu)")},
             "k2_simple_kernel": {"class": "OPAQUE+U", "launch_ms": ms_simple, "algorithmic_bytes": alg_simple,
                                  "achieved_gbs": alg_simple / (ms_simple * 1e-3) / 1e9 if ms_simple else None,
                                  "traffic": traffic.get("k2_simple_kernel"),
                                  "note": "write-only on this workload (cudaMemset reaches 3.9 TB/s on the same box, profiles/microbench/hbm_rw.txt)"},
         }
-        dom = "k2_generic_kernel" if ms_generic >= ms_simple else "k2_simple_kernel"
+        dom = g_name if ms_generic >= ms_simple else "k2_simple_kernel"
         dom_gbs = kernels[dom]["achieved_gbs"] or 0.0
         blocks_all = n_total * blocks_per_image * args.steps
         line = {
@@ -792,7 +822,8 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
                          "launch_ms": kernels[dom]["launch_ms"], "peak_source": peak_src,
                          "timing": "CUDA events on the launching stream around the kernel alone (other class group masked off), mean of the timed steps",
                          "step": {"achieved": achieved, "frac": achieved / peak, "algorithmic_bytes": alg_bytes, "ms": launch_ms,
-                                  "what": "whole K2 step = k2_generic_kernel with k2_simple_kernel beside it on a side stream (one small CTA per SM fits next to the G kernel's three), joined before the step ends"},
+                                  "what": "whole K2 step = the G-class kernel, then k2_simple_kernel (the operator kernel fills every SM's shared memory, so the two run one after the other; "
+                                          "with the fp32 G kernel the simple kernel runs beside it on a side stream)"},
                          "kernels": kernels},
             "parity": parity,
             "per_image_compile_and_blend": per_image,
@@ -807,6 +838,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
                     "images_per_step_per_gpu": n_e2e, "steps": e2e_steps,
                     "path": "mjx_compose_batch_host on page-locked host planes: one K2 launch reads/writes the touched blocks over PCIe (zero-copy)",
                     "timing": "wall clock around mjx_compose_batch_host, max over ranks", "gpu_launches": e2e_launches,
+                    "host_copy": host_copy,
                     "staged": {"value": e2e_staged_mbps, "unit": "Mblocks/s", "h2d_bytes_per_step": n_e2e * (roi_bytes + 608),
                                "d2h_bytes_per_step": n_e2e * roi_bytes,
                                "path": "same call with zero-copy off: region under the dropon copied H2D, blended, copied D2H (3-stream pipeline)"}},
@@ -827,7 +859,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--images-per-gpu", type=int, default=1250)
     ap.add_argument("--e2e-images", type=int, default=1250)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-kernels", action="store_true")
     ap.add_argument("--no-parity", action="store_true")

@@ -171,6 +171,9 @@ typedef struct {
 
 int mj_compose_batch(int n, const mj_blob_t *in, mj_blob_t *out, int *status, mj_dropon_t *d, unsigned int align, int offset_x,
                      int offset_y, int write_options, int nthreads);
+/* GPUs mj_compose_batch spreads a batch over (images are independent: one contiguous slice, one group of host threads, one
+ * compiled dropon per device; nothing crosses between devices).  0 = take $MJX_DEVICES ("all" or a count), default 1. */
+void mj_batch_set_devices(int devices);
 
 /* ---- additive: request coalescer (not in the reference) ---------------------------------
  * For request servers (the nginx filter's shape: many threads, one image per call, one shared logo).  When enabled,

@@ -29,6 +29,8 @@ int mjx_jpeg_layout(mj_jpeg_t *m, mjx_layout_t *layout);
 /* the calling thread's engine context (created on first use; device from $MJX_DEVICE, default 0).
  * Returns NULL and prints one line to stderr when no CUDA device is usable. */
 mjx_ctx *mjx_host_ctx(void);
+/* device of the calling thread's context, for threads that have not made a compute call yet (-1: $MJX_DEVICE or 0) */
+void mjx_host_set_device(int device);
 
 #ifdef __cplusplus
 }

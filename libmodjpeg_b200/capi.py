@@ -217,6 +217,8 @@ class Engine:
                                f"({self.lib.mjx_device_count()} visible); the engine has no CPU fallback")
         self.ctx = ctx
         self.device = device
+        env = os.environ.get("MJX_K2_TC")
+        self._tc_mode = 1 if env is None else max(0, min(2, int(env)))  # the ctx's initial mode (mjx_ctx_create)
 
     def close(self) -> None:
         if getattr(self, "ctx", None):
@@ -264,6 +266,11 @@ class Engine:
         """G class of batches of >= 256 images: 1 tensor-core kernel with coefficient range check (default), 2 without
         check, 0 fp32 kernel"""
         self._check(self.lib.mjx_ctx_set_tensor_core(self.ctx, mode), "mjx_ctx_set_tensor_core")
+        self._tc_mode = mode
+
+    def tensor_core_active(self, n_images: int, generic_blocks: int) -> bool:
+        """does a batch of n_images take the tensor-core G kernel (mode set, batch large enough, class G present)?"""
+        return self._tc_mode != 0 and n_images >= 256 and generic_blocks > 0
 
     def set_operator_pieces(self, pieces: int) -> None:
         """fp16 pieces per entry of the tensor-core kernel's operator (2 or 3); for dropons not yet used in a large batch"""
@@ -445,6 +452,8 @@ def load_modjpeg() -> C.CDLL:
     L.mjx_jpeg_export_plane.argtypes = [vp, C.c_int, vp]
     L.mjx_jpeg_import_plane.argtypes = [vp, C.c_int, vp]
     L.mjx_jpeg_layout.argtypes = [vp, C.POINTER(Layout)]
+    L.mj_batch_set_devices.argtypes = [C.c_int]
+    L.mj_batch_set_devices.restype = None
     L.mj_coalesce_configure.argtypes = [C.c_int, C.c_int, C.c_int]
     L.mj_coalesce_configure.restype = None
     L.mj_coalesce_stats.argtypes = [C.POINTER(C.c_ulong), C.POINTER(C.c_ulong)]
@@ -564,6 +573,11 @@ class Jpeg:
 class Blob(C.Structure):
     """mj_blob_t (include/libmodjpeg.h)"""
     _fields_ = [("data", C.c_void_p), ("len", C.c_size_t)]
+
+
+def batch_set_devices(devices: int) -> None:
+    """GPUs mj_compose_batch spreads a batch over (0: $MJX_DEVICES, default 1)"""
+    load_modjpeg().mj_batch_set_devices(devices)
 
 
 def coalesce_configure(enable: bool, max_batch: int = 0, wait_us: int = -1) -> None:

@@ -38,6 +38,7 @@ typedef struct {
     int             ncomp;
     mjx_geometry_t  g;
     int             write_options;
+    double          phase_s[5]; /* MJ_BATCH_TRACE=1: seconds per phase ([0] = K2) */
 } batch_t;
 
 static int take(batch_t *b, int limit) {
@@ -108,8 +109,6 @@ static void *worker(void *arg) {
     return NULL;
 }
 
-static double g_phase_s[5]; /* MJ_BATCH_TRACE=1: seconds spent per phase (diagnostic, not thread-safe across batches) */
-
 static double now_s(void) {
     struct timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -120,10 +119,14 @@ static void run_phase(batch_t *b, int phase, int nthreads, pthread_t *th) {
     const double t0 = now_s();
     b->phase = phase;
     b->next = 0;
-    for(int t = 1; t < nthreads; t++) pthread_create(&th[t], NULL, worker, b);
+    int started = 1;
+    for(int t = 1; t < nthreads; t++) {
+        if(pthread_create(&th[started], NULL, worker, b) != 0) break; /* fewer helpers: the tasks are taken by whoever runs */
+        started++;
+    }
     worker(b); /* the calling thread works too */
-    for(int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
-    g_phase_s[phase] += now_s() - t0;
+    for(int t = 1; t < started; t++) pthread_join(th[t], NULL);
+    b->phase_s[phase] += now_s() - t0;
 }
 
 static int same_geometry(const mj_jpeg_t *a, const mj_jpeg_t *b) {
@@ -137,22 +140,13 @@ static int same_geometry(const mj_jpeg_t *a, const mj_jpeg_t *b) {
     return 1;
 }
 
-int mj_compose_batch(int n, const mj_blob_t *in, mj_blob_t *out, int *status, mj_dropon_t *d, unsigned int align, int offset_x,
-                     int offset_y, int write_options, int nthreads) {
-    if(n < 0 || (n > 0 && (in == NULL || out == NULL || status == NULL)) || d == NULL) return MJ_ERR_NULL_DATA;
-    if(nthreads < 1) nthreads = 1;
-    if(nthreads > 256) nthreads = 256;
-    for(int i = 0; i < n; i++) {
-        out[i].data = NULL;
-        out[i].len = 0;
-        status[i] = MJ_OK;
-    }
-    if(n == 0) return MJ_OK;
+/* the pipeline on the calling thread's device */
+static int batch_on_device(int n, const mj_blob_t *in, mj_blob_t *out, int *status, mj_dropon_t *d, unsigned int align, int offset_x,
+                           int offset_y, int write_options, int nthreads) {
     const int compose = d->blend != MJ_BLEND_NONE && d->image != NULL && d->alpha != NULL;
     mjx_ctx  *ctx = compose ? mjx_host_ctx() : NULL;
     if(compose && ctx == NULL) return MJ_ERR_DEVICE;
 
-    memset(g_phase_s, 0, sizeof(g_phase_s));
     int window = 4 * nthreads;
     if(window > 256) window = 256;
     if(window > n) window = n;
@@ -240,7 +234,7 @@ int mj_compose_batch(int n, const mj_blob_t *in, mj_blob_t *out, int *status, mj
                 if(ok) {
                     const double tk = now_s();
                     rv = mjx_compose_batch_host(ctx, items, b.ngroup, cd, 0, 0); /* K2: one launch for the group */
-                    g_phase_s[0] += now_s() - tk;
+                    b.phase_s[0] += now_s() - tk;
                     if(rv != MJX_OK) fprintf(stderr, "libmodjpeg (B200): batch compose failed: %s\n", mjx_ctx_last_error(ctx));
                     rv = mjp_map_error(rv);
                 }
@@ -255,7 +249,7 @@ int mj_compose_batch(int n, const mj_blob_t *in, mj_blob_t *out, int *status, mj
     }
     if(getenv("MJ_BATCH_TRACE") != NULL)
         fprintf(stderr, "mj_compose_batch: %d images, %d threads: decode %.3f s, stage-in %.3f s, K2 %.3f s, stage-out %.3f s, encode %.3f s\n", n,
-                nthreads, g_phase_s[1], g_phase_s[2], g_phase_s[0], g_phase_s[3], g_phase_s[4]);
+                nthreads, b.phase_s[1], b.phase_s[2], b.phase_s[0], b.phase_s[3], b.phase_s[4]);
 out:
     if(cd != NULL) mjx_dropon_free(cd);
     free(b.jp);
@@ -264,5 +258,80 @@ out:
     free(th);
     free(items);
     pthread_mutex_destroy(&b.lock);
+    return result;
+}
+
+/* ---- several devices from one process -------------------------------------------------------------------------------------
+ * Images are independent (reference: src/compose.c:256-339 keeps no state between blocks), so the batch is cut into
+ * one contiguous slice per device; every slice runs the pipeline above on its own group of host threads, whose engine contexts
+ * (stream, staging pools, page-locked slab) and compiled dropon live on that device.  No data crosses between devices. */
+static int g_devices = 0; /* 0: $MJX_DEVICES ("all" or a count), default 1 */
+
+void mj_batch_set_devices(int devices) { __atomic_store_n(&g_devices, devices < 0 ? 0 : devices, __ATOMIC_RELAXED); }
+
+static int batch_devices(void) {
+    int want = __atomic_load_n(&g_devices, __ATOMIC_RELAXED);
+    if(want == 0) {
+        const char *e = getenv("MJX_DEVICES");
+        if(e == NULL || !*e) return 1;
+        want = strcmp(e, "all") == 0 ? 1 << 20 : atoi(e);
+    }
+    const int have = mjx_device_count();
+    if(want > have) want = have;
+    return want < 1 ? 1 : want;
+}
+
+typedef struct {
+    int              device, n, nthreads, rv;
+    const mj_blob_t *in;
+    mj_blob_t       *out;
+    int             *status;
+    mj_dropon_t     *d;
+    unsigned int     align;
+    int              offset_x, offset_y, write_options;
+} slice_t;
+
+static void *slice_main(void *arg) {
+    slice_t *s = (slice_t *)arg;
+    mjx_host_set_device(s->device); /* this thread's context (created inside) lives on the slice's device */
+    s->rv = batch_on_device(s->n, s->in, s->out, s->status, s->d, s->align, s->offset_x, s->offset_y, s->write_options, s->nthreads);
+    return NULL;
+}
+
+int mj_compose_batch(int n, const mj_blob_t *in, mj_blob_t *out, int *status, mj_dropon_t *d, unsigned int align, int offset_x,
+                     int offset_y, int write_options, int nthreads) {
+    if(n < 0 || (n > 0 && (in == NULL || out == NULL || status == NULL)) || d == NULL) return MJ_ERR_NULL_DATA;
+    if(nthreads < 1) nthreads = 1;
+    if(nthreads > 256) nthreads = 256;
+    for(int i = 0; i < n; i++) {
+        out[i].data = NULL;
+        out[i].len = 0;
+        status[i] = MJ_OK;
+    }
+    if(n == 0) return MJ_OK;
+    int ndev = batch_devices();
+    if(ndev > nthreads) ndev = nthreads;
+    if(ndev > n) ndev = n;
+    if(ndev <= 1) return batch_on_device(n, in, out, status, d, align, offset_x, offset_y, write_options, nthreads);
+    slice_t   sl[64];
+    pthread_t th[64];
+    char      joined[64];
+    if(ndev > 64) ndev = 64;
+    int result = MJ_OK, lo = 0;
+    for(int k = 0; k < ndev; k++) {
+        const int cnt = n / ndev + (k < n % ndev ? 1 : 0);
+        slice_t  *s = &sl[k];
+        s->device = k, s->n = cnt, s->in = in + lo, s->out = out + lo, s->status = status + lo, s->d = d, s->align = align;
+        s->offset_x = offset_x, s->offset_y = offset_y, s->write_options = write_options, s->rv = MJ_OK;
+        s->nthreads = nthreads / ndev + (k < nthreads % ndev ? 1 : 0);
+        lo += cnt;
+        joined[k] = pthread_create(&th[k], NULL, slice_main, s) == 0;
+        if(!joined[k]) /* no thread to be had: the caller does this slice itself, on its own device */
+            s->rv = batch_on_device(s->n, s->in, s->out, s->status, s->d, s->align, s->offset_x, s->offset_y, s->write_options, s->nthreads);
+    }
+    for(int k = 0; k < ndev; k++) {
+        if(joined[k]) pthread_join(th[k], NULL);
+        if(sl[k].rv != MJ_OK && result == MJ_OK) result = sl[k].rv;
+    }
     return result;
 }

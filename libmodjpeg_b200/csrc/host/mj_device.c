@@ -11,6 +11,7 @@
 #include "mj_private.h"
 
 static pthread_key_t  g_key;
+static __thread int   t_device = -1; /* mjx_host_set_device: this thread's device, -1 = $MJX_DEVICE or 0 */
 static pthread_once_t g_once = PTHREAD_ONCE_INIT;
 
 static void ctx_destructor(void *p) {
@@ -25,7 +26,8 @@ mjx_ctx *mjx_host_ctx(void) {
     if(ctx != NULL) return ctx;
     int         device = 0;
     const char *env = getenv("MJX_DEVICE");
-    if(env != NULL && *env) device = atoi(env);
+    if(t_device >= 0) device = t_device;
+    else if(env != NULL && *env) device = atoi(env);
     int rv = mjx_ctx_create(&ctx, device);
     if(rv != MJX_OK || ctx == NULL) {
         fprintf(stderr, "libmodjpeg (B200): no usable CUDA device %d (%d devices visible) - mj_compose/mj_effect_* need the GPU engine, there is no CPU fallback\n",
@@ -35,3 +37,7 @@ mjx_ctx *mjx_host_ctx(void) {
     pthread_setspecific(g_key, ctx);
     return ctx;
 }
+
+/* The device the calling thread's context is created on (before its first compute call; a thread that already has a
+ * context keeps it).  mj_compose_batch uses it to give each device its own group of host threads. */
+void mjx_host_set_device(int device) { t_device = device; }

@@ -650,7 +650,7 @@ static const OpView *dropon_op_cache(mjx_ctx *ctx, const mjx_dropon *cd, int n) 
 
 // one K2 launch with the ctx's settings on stream `st`; `scratch` holds k2_scratch_bytes(n, view) bytes
 static cudaError_t run_k2(mjx_ctx *ctx, cudaStream_t st, void *scratch, const mjx_image_desc_t *items_dev, int n, const mjx_dropon *d,
-                          int block_x, int block_y, bool with_side) {
+                          int block_x, int block_y, bool with_side, bool planes_in_hbm = true) {
     const K2Side side = {ctx->side_stream, ctx->side_fork, ctx->side_join};
     int          launches = 0;
     K2Launch     L;
@@ -660,7 +660,9 @@ static cudaError_t run_k2(mjx_ctx *ctx, cudaStream_t st, void *scratch, const mj
     L.sm_count = ctx->sm_count;
     L.class_mask = ctx->class_mask;
     L.tc = ctx->k2_tc;
-    L.op = with_side ? dropon_op_cache(ctx, d, n) : nullptr; // batch entry points only
+    // the tensor-core kernel: batch entry points only, and only for planes in device memory -- its gather (one block per image and
+    // request, past L1) is made for HBM; over PCIe the fp32 kernel's runs of neighbouring blocks move twice as much per second
+    L.op = with_side && planes_in_hbm ? dropon_op_cache(ctx, d, n) : nullptr;
     L.side = with_side && ctx->overlap ? &side : nullptr;
     L.dev = &ctx->k2dev;
     L.launches = &launches;
@@ -784,7 +786,7 @@ int mjx_compose_batch_host(mjx_ctx *ctx, const mjx_host_image_t *items, int n, c
                     memcpy(desc[i].q[c], items[i].q[c], 128);
                 }
             MJX_CUDA(ctx, cudaMemcpyAsync(ctx->desc_dev, desc, dbytes, cudaMemcpyHostToDevice, ctx->stream));
-            const cudaError_t e = run_k2(ctx, ctx->stream, ctx->scratch, (const mjx_image_desc_t *)ctx->desc_dev, n, d, block_x, block_y, true);
+            const cudaError_t e = run_k2(ctx, ctx->stream, ctx->scratch, (const mjx_image_desc_t *)ctx->desc_dev, n, d, block_x, block_y, true, false);
             if(e != cudaSuccess) return fail(ctx, e, "k2_compose_kernel");
             MJX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             return MJX_OK;

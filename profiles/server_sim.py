@@ -76,9 +76,31 @@ def case(name, data, raw, align, ox, oy, threads, seconds):
             j.free()
         return req
 
+    def compose_only():
+        # the compose call alone on an already decoded image (what the coalescer can change; entropy coding is libjpeg's)
+        def req():
+            if not hasattr(req, "j"):
+                req.j = M.Jpeg()
+                assert req.j.read_jpeg_from_memory(data) == 0
+            assert req.j.compose(d, align, ox, oy) == 0
+        return req
+
+    from libmodjpeg_b200 import capi
+
     res = {"config": name, "threads": threads, "seconds": seconds, "dropon_cache": os.environ.get("MJX_DROPON_CACHE", "0")}
     for label, n in (("1_thread", 1), ("all_threads", threads)):
         res[label] = {"b200_requests_per_s": run(n, seconds, ours), "reference_requests_per_s": run(n, seconds, theirs)}
+    res["all_threads"]["b200_compose_calls_per_s"] = run(threads, seconds, compose_only)
+    # the same load with the request coalescer on (mj_coalesce_configure: concurrent calls share one launch and one compiled dropon)
+    b0, r0 = capi.coalesce_stats()
+    capi.coalesce_configure(True, threads, 150)
+    try:
+        res["all_threads"]["b200_coalesced_requests_per_s"] = run(threads, seconds, ours)
+        res["all_threads"]["b200_coalesced_compose_calls_per_s"] = run(threads, seconds, compose_only)
+    finally:
+        capi.coalesce_configure(False)
+    b1, r1 = capi.coalesce_stats()
+    res["all_threads"]["coalescer"] = {"requests": r1 - r0, "launches": b1 - b0, "max_batch": threads, "wait_us": 150}
     return res
 
 

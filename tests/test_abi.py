@@ -29,7 +29,7 @@ def test_libmodjpeg_exports_reference_api(built):
     lib = C.CDLL(built["libmodjpeg"])
     names = _declared("libmodjpeg.h", "mj_")
     # the reference's 16 public functions (reference: src/libmodjpeg.h:129-149) + the additive batch pipeline and coalescer
-    additive = ["mj_compose_batch", "mj_coalesce_configure", "mj_coalesce_stats"]
+    additive = ["mj_compose_batch", "mj_batch_set_devices", "mj_coalesce_configure", "mj_coalesce_stats"]
     assert all(a in names for a in additive)
     names = [n for n in names if n not in additive]
     assert names == sorted(["mj_init_dropon", "mj_read_dropon_from_raw", "mj_read_dropon_from_memory", "mj_read_dropon_from_file",

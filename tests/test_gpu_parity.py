@@ -650,6 +650,28 @@ def test_api_threads_are_independent(engine):
             assert np.array_equal(a, b)
 
 
+def test_compose_batch_over_two_devices(engine):
+    """mj_compose_batch with the batch cut into one slice per GPU (one process, a group of host threads and a compiled dropon
+    per device): byte-identical outputs to the single-device run"""
+    import libmodjpeg_b200 as M
+    from libmodjpeg_b200 import capi
+
+    if capi.load_mjx().mjx_device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    datas = [util.jpeg_bytes(320, 240, "420", 85, seed=80 + i) for i in range(5)]
+    batch = [datas[i % 5] for i in range(37)]
+    d = M.Dropon()
+    assert d.read_dropon_from_raw(util.logo_rgba(160, 120, 32, 13), M.CS_RGBA, 255) == 0
+    rv1, st1, out1 = capi.compose_batch(batch, d, M.ALIGN_CENTER, 3, 5, 0, nthreads=8)
+    capi.batch_set_devices(2)
+    try:
+        rv2, st2, out2 = capi.compose_batch(batch, d, M.ALIGN_CENTER, 3, 5, 0, nthreads=8)
+    finally:
+        capi.batch_set_devices(1)
+    assert rv1 == 0 and rv2 == 0 and not any(st1) and not any(st2)
+    assert all(a == b for a, b in zip(out1, out2))
+
+
 def test_coalesced_compose_equals_unbatched(engine):
     """request coalescer: 8 threads composing different images with ONE dropon, at two placements and on
     two image sizes (different keys must not share a batch) -- byte-identical to the unbatched calls, fewer launches than
