@@ -6,7 +6,7 @@
 //
 // The arithmetic is libjpeg-turbo 3.1.x's integer pipeline restated: jccolor.c
 // rgb_ycc_convert, jcsample.c fullsize/h2v1/h2v2/int_downsample, jfdctint.c jpeg_fdct_islow,
-// q == 1 quantisation -- bit-exact against the reference build (tests/test_k1_parity.py).
+// q == 1 quantisation -- bit-exact against the reference build (tests/test_gpu_parity.py::test_k1_compile_bitexact_vs_oracle).
 //
 // Work unit = one output block of one component, 8 lanes, lane r = sample row r.  The padded
 // canvas of src/dropon.c:352-369 is never materialised: canvas pixels are fetched from the

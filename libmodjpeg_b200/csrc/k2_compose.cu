@@ -70,7 +70,6 @@ __global__ void __launch_bounds__(kThreads) k2_strict_kernel(const StrictParams 
 
     const uint32_t meta = __ldg(dc.meta + bi);
     const uint32_t cls = meta_cls(meta);
-    if(cls == CLS_T) return;
 
     const mjx_image_desc_t &im = p.items[blockIdx.y];
     const int l = bi / dc.wb, k = bi - l * dc.wb;
@@ -101,6 +100,19 @@ __global__ void __launch_bounds__(kThreads) k2_strict_kernel(const StrictParams 
 
     int I[8];
     row_unpack(ld_row_stream(ip), I);
+
+    if(cls == CLS_T) {
+        // all-zero alpha: the reference still dequantises and requantises the block in place (src/compose.c:277-286, 327-336), which
+        // is the identity unless I*q leaves int16 -- the case this kernel exists for
+        bool changed = false;
+#pragma unroll
+        for(int i = 0; i < 8; i++) {
+            out[i] = wrap16(tdiv(wrap16(I[i] * q[i]), rq[i]));
+            changed = changed || out[i] != I[i];
+        }
+        if(changed) st_row_stream(ip, row_pack(out));
+        return;
+    }
 
     if(cls == CLS_U) {
         const float w4 = uniform_w4(meta_wdc(meta));

@@ -53,7 +53,7 @@ __device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
     for(int spin = 0; spin < (1 << 26); spin++) {
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if(ok) return;
+        if(ok) return; // (a nanosleep(100) between polls: 1.62 instead of 1.50 ms on the bench batch -- the UMMAs must go out at once)
     }
     __trap();
 }

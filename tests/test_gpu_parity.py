@@ -729,8 +729,10 @@ def test_k2_strict_mode_reproduces_int16_wraparound(engine, port):
     q = [rng.integers(20, 256, 64).astype(np.uint16) for _ in range(3)]
     try:
         engine.set_strict(True)
+        clear = util.noisy_rgba(96, 64, 4)
+        clear[:, :, 3] = 0  # alpha 0 everywhere: class T, which the reference still dequantises and requantises in place
         for name, raw, cs, blend in [("uniform", util.noisy_rgba(96, 64, 1)[:, :, :3], 1, 100), ("opaque", util.noisy_rgba(96, 64, 2)[:, :, :3], 1, 255),
-                                     ("generic", util.noisy_rgba(96, 64, 3), 2, 255)]:
+                                     ("transparent", clear, 2, 255), ("generic", util.noisy_rgba(96, 64, 3), 2, 255)]:
             i3, a3, scs, sblend = util.ingest_raw(raw, cs, blend)
             rv, D, Wc = port.compile_dropon(i3, a3, scs, O.make_layout(3, samp))
             assert rv == 0
