@@ -117,6 +117,9 @@ int         mjx_ctx_set_strict(mjx_ctx *ctx, int strict);
  * Env MJX_K2_TC sets the initial mode.  The cache (16 or 24 KB per class G block, MJX_K2_OP_MAX_MB caps it, default 4096)
  * belongs to the first ctx that uses the dropon this way; other ctxs run the fp32 kernel with it. */
 int         mjx_ctx_set_tensor_core(mjx_ctx *ctx, int mode);
+/* smallest batch that takes the tensor-core kernel (>= 256; default 1025): the kernel deals batches of 64 images to three
+ * groups of warps, so a batch of a few hundred images leaves groups idle and the fp32 kernel is the faster one. */
+int         mjx_ctx_set_tensor_core_min_images(mjx_ctx *ctx, int n);
 /* fp16 pieces per operator entry: 2 (22 significant bits) is the only value the kernel is built for -- it reproduces the
  * reference on every test image (tests/test_gpu_tensor_core.py); the call exists so that a build with more pieces stays
  * source compatible. */

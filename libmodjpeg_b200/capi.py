@@ -98,6 +98,7 @@ def load_mjx() -> C.CDLL:
     L.mjx_ctx_use_own_stream.argtypes = [vp]
     L.mjx_ctx_set_strict.argtypes = [vp, C.c_int]
     L.mjx_ctx_set_tensor_core.argtypes = [vp, C.c_int]
+    L.mjx_ctx_set_tensor_core_min_images.argtypes = [vp, C.c_int]
     L.mjx_ctx_set_operator_pieces.argtypes = [vp, C.c_int]
     L.mjx_ctx_stream.argtypes = [vp]
     L.mjx_ctx_stream.restype = vp
@@ -268,9 +269,14 @@ class Engine:
         self._check(self.lib.mjx_ctx_set_tensor_core(self.ctx, mode), "mjx_ctx_set_tensor_core")
         self._tc_mode = mode
 
+    def set_tensor_core_min_images(self, n: int) -> None:
+        """smallest batch that takes the tensor-core G kernel (>= 256; default 1025)"""
+        self._check(self.lib.mjx_ctx_set_tensor_core_min_images(self.ctx, n), "mjx_ctx_set_tensor_core_min_images")
+        self._tc_min = n
+
     def tensor_core_active(self, n_images: int, generic_blocks: int) -> bool:
         """does a batch of n_images take the tensor-core G kernel (mode set, batch large enough, class G present)?"""
-        return self._tc_mode != 0 and n_images >= 256 and generic_blocks > 0
+        return self._tc_mode != 0 and n_images >= getattr(self, "_tc_min", 1025) and generic_blocks > 0
 
     def set_operator_pieces(self, pieces: int) -> None:
         """fp16 pieces per entry of the tensor-core kernel's operator (2 or 3); for dropons not yet used in a large batch"""

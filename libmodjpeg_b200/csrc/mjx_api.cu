@@ -601,6 +601,12 @@ int mjx_ctx_set_tensor_core(mjx_ctx *ctx, int mode) {
     return MJX_OK;
 }
 
+int mjx_ctx_set_tensor_core_min_images(mjx_ctx *ctx, int n) {
+    if(!ctx || n < kOpMinImages) return MJX_ERR_ARG;
+    ctx->k2_op_min_images = n;
+    return MJX_OK;
+}
+
 int mjx_ctx_set_operator_pieces(mjx_ctx *ctx, int pieces) {
     if(!ctx || pieces != 2) return MJX_ERR_ARG; // the kernel's shared-memory budget holds two pieces per operator
     ctx->k2_op_pieces = pieces;
@@ -622,7 +628,7 @@ int mjx_ctx_set_strict(mjx_ctx *ctx, int strict) {
 // the dropon's operator cache for the tensor-core G kernel, if this ctx may use it (allocated on first use)
 static const OpView *dropon_op_cache(mjx_ctx *ctx, const mjx_dropon *cd, int n) {
     mjx_dropon *d = const_cast<mjx_dropon *>(cd); // the cache is the one mutable part of a compiled dropon
-    if(!ctx->k2_tc || ctx->strict || n < kOpMinImages || d->view.n_generic <= 0) return nullptr;
+    if(!ctx->k2_tc || ctx->strict || n < kOpMinImages || n < ctx->k2_op_min_images || d->view.n_generic <= 0) return nullptr;
     mjx_ctx *none = nullptr;
     if(d->op_owner.compare_exchange_strong(none, ctx)) {
         const size_t bytes = op_cache_bytes(d->view.n_generic, ctx->k2_op_pieces, nullptr);

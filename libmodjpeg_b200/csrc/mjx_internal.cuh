@@ -60,6 +60,10 @@ struct K2Dev {
 // batches of at least this many images take the tensor-core G kernel (k2_generic_op.cu): below it the operator pieces
 // (16-24 KB per dropon block and launch) outweigh what the fp32 kernel costs
 static constexpr int kOpMinImages = 256;
+// ... and by default only batches from this size on: the kernel deals batches of 64 images round-robin to three groups of warps,
+// so a small batch leaves groups idle (256 images: 2 + 1 + 1 batches, a third of the tensor-core kernel's time is waiting;
+// c2 with 256 images: 0.233 ms against 0.200 ms on the fp32 kernel).  From 17 batches on at most 1 in 10 group slots is empty.
+static constexpr int kOpDefaultMinImages = 1025;
 struct OpView;
 } // namespace mjx
 
@@ -120,6 +124,7 @@ struct mjx_ctx {
     cudaEvent_t  side_fork = nullptr, side_join = nullptr;
     int          overlap = 1;
     int          k2_tc = 1; // G class of batches of >= kOpMinImages images on the tensor-core kernel: 1 with range check, 2 without, 0 off
+    int          k2_op_min_images = mjx::kOpDefaultMinImages; // mjx_ctx_set_tensor_core_min_images
     int          k2_op_pieces = 2;     // fp16 pieces per operator entry (MJX_K2_OP_PIECES: 2 or 3)
     size_t       k2_op_max_bytes = (size_t)4 << 30; // largest operator cache a dropon may get (MJX_K2_OP_MAX_MB)
     mjx::K2Dev   k2dev;

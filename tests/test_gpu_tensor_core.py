@@ -18,6 +18,15 @@ pytestmark = pytest.mark.gpu
 OP_MIN_IMAGES = 256  # libmodjpeg_b200/csrc/mjx_internal.cuh: kOpMinImages
 
 
+@pytest.fixture(autouse=True)
+def _op_kernel_from_256_images(engine):
+    """the kernel serves batches from 256 images on; by default it is only CHOSEN from 1025 on (smaller batches leave its warp
+    groups idle and the fp32 kernel is faster) -- the tests want it on their small batches"""
+    engine.set_tensor_core_min_images(OP_MIN_IMAGES)
+    yield
+    engine.set_tensor_core_min_images(1025)
+
+
 def _run(engine, batch, dec_planes, cd, g, mode, expect_op=None):
     for i, planes in enumerate(dec_planes):
         batch.upload_image(i, planes)
@@ -58,6 +67,7 @@ def test_operator_kernel_vs_oracle_and_fp32(built, port, subs, gray, quality, ni
     from libmodjpeg_b200.batch import DeviceBatch
 
     engine = Engine(0)  # own ctx: the operator cache of a dropon belongs to the first ctx that uses it
+    engine.set_tensor_core_min_images(OP_MIN_IMAGES)
     engine.set_operator_pieces(pieces)
     W_, H_ = 208, 144
     uniq = [_decode(util.jpeg_bytes(W_, H_, subs, quality, seed=700 + i, gray=gray)) for i in range(5)]
