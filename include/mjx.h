@@ -196,6 +196,35 @@ int mjx_compose_batch_host(mjx_ctx *ctx, const mjx_host_image_t *items, int n, c
 int mjx_compose_rows_host(mjx_ctx *ctx, int ncomp, int16_t *const *const *rows, const uint16_t *const *q,
                           const mjx_dropon *d);
 
+/* ---- K4: Huffman coding of a baseline scan on the device -----------------------------------------
+ *      replaces, for mj_write_jpeg_to_memory (reference: src/image.c:120-209), the entropy encoder that
+ *      jpeg_write_coefficients / jpeg_finish_compress run on the host (libjpeg jctrans.c compress_output, jchuff.c
+ *      encode_mcu_huff): sequential DCT, Huffman tables as given (not optimised), no restart markers, ONE scan holding
+ *      every component.  Byte-identical to libjpeg's entropy-coded segment. */
+typedef struct {
+    uint8_t bits[17];  /* bits[k] = number of codes of length k, k = 1..16 (JHUFF_TBL.bits, the DHT segment's list) */
+    uint8_t vals[256]; /* the symbols in order of increasing code length (JHUFF_TBL.huffval) */
+} mjx_huff_table_t;
+typedef struct {
+    int32_t          ncomp;                                          /* components of the scan = of the image, in order */
+    int32_t          h_samp[MJX_MAX_COMPONENTS], v_samp[MJX_MAX_COMPONENTS]; /* (ignored when ncomp == 1: not interleaved) */
+    int32_t          dc_tbl[MJX_MAX_COMPONENTS], ac_tbl[MJX_MAX_COMPONENTS]; /* which of dc[] / ac[] a component uses */
+    int32_t          mcus_per_row, mcu_rows;                         /* ncomp == 1: the component's width / height in blocks */
+    mjx_huff_table_t dc[4], ac[4];                                   /* unused tables: all zero */
+} mjx_scan_t;
+/* n images resident in HBM (planes as for K2; wreal / hreal of the descriptors say where the encoder's dummy blocks start).
+ * Image i's segment -- byte-stuffed, last byte padded with 1-bits, no EOI -- goes to out_dev + i * out_stride, its length to
+ * sizes_dev[i]; 0xFFFFFFFF there means "not coded": a coefficient the tables cannot code (DC difference beyond 11 bits, AC
+ * beyond 10: libjpeg's JERR_BAD_DCT_COEF), a symbol without a code, or a segment longer than out_stride.  Asynchronous on
+ * the ctx stream. */
+int mjx_huffman_encode_batch_device(mjx_ctx *ctx, const mjx_image_desc_t *items_dev, int n, const mjx_scan_t *scan,
+                                    void *out_dev, size_t out_stride, uint32_t *sizes_dev);
+/* one image as libjpeg row pointers: rows[c][l] -> block (l, 0) of component c, l in [0, hreal[c]), stride_blocks[c] blocks
+ * per row.  *out is malloc()ed (the caller frees it).  MJX_ERR_UNSUPPORTED: not codable, see above. */
+int mjx_huffman_encode_rows_host(mjx_ctx *ctx, int ncomp, const int16_t *const *const *rows, const int *stride_blocks,
+                                 const int *vrows, const int *wreal, const int *hreal, const mjx_scan_t *scan,
+                                 unsigned char **out, size_t *len);
+
 /* ---- K3: coefficient effects (replaces src/effect.c:28-222) --------------------------- */
 int mjx_effects_batch_device(mjx_ctx *ctx, const mjx_image_desc_t *items_dev, int n, int ncomp,
                              const mjx_effect_op_t *ops, int nops);

@@ -26,6 +26,11 @@ int mjx_jpeg_export_plane(mj_jpeg_t *m, int c, short *dst);
 int mjx_jpeg_import_plane(mj_jpeg_t *m, int c, const short *src);
 /* the target layout of a decoded JPEG, as K1 wants it */
 int mjx_jpeg_layout(mj_jpeg_t *m, mjx_layout_t *layout);
+/* mj_write_jpeg_to_memory with the entropy coding done on the device (K4, mjx_huffman_encode_rows_host): libjpeg writes
+ * the markers, the kernels the scan; byte-identical to mj_write_jpeg_to_memory(m, .., 0).  Baseline only: MJ_ERR_UNSUPPORTED_FILETYPE
+ * for MJ_OPTION_OPTIMIZE / _PROGRESSIVE / _ARITHMETRIC and for coefficients Huffman tables cannot code.  With MJX_GPU_HUFFMAN=1 in
+ * the environment mj_write_jpeg_to_memory takes this path by itself and falls back to libjpeg where it does not apply. */
+int mjx_write_jpeg_to_memory_device(mj_jpeg_t *m, unsigned char **memory, size_t *len, int options);
 /* the calling thread's engine context (created on first use; device from $MJX_DEVICE, default 0).
  * Returns NULL and prints one line to stderr when no CUDA device is usable. */
 mjx_ctx *mjx_host_ctx(void);

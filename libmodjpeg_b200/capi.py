@@ -137,6 +137,7 @@ def load_mjx() -> C.CDLL:
     L.mjx_compose_batch_device.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int]
     L.mjx_compose_batch_host.argtypes = [vp, C.POINTER(HostImage), C.c_int, vp, C.c_int, C.c_int]
     L.mjx_compose_rows_host.argtypes = [vp, C.c_int, vp, vp, vp]
+    L.mjx_huffman_encode_batch_device.argtypes = [vp, vp, C.c_int, vp, vp, C.c_size_t, vp]
     L.mjx_effects_batch_device.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(EffectOp), C.c_int]
     L.mjx_effects_rows_host.argtypes = [vp, C.c_int, vp, ip, ip, vp, C.POINTER(EffectOp), C.c_int]
     _lib_mjx = L
@@ -378,6 +379,77 @@ class Engine:
         self._check(self.lib.mjx_effects_batch_device(self.ctx, C.c_void_p(items_dev), n, ncomp, arr, len(ops)),
                     "mjx_effects_batch_device")
 
+    # ---- K4 -----------------------------------------------------------------------------
+    def huffman_encode_batch_device(self, items_dev: int, n: int, scan: "Scan", out_dev: int, out_stride: int, sizes_dev: int) -> None:
+        """entropy-coded segments of n device-resident images (asynchronous on the ctx stream)"""
+        self._check(self.lib.mjx_huffman_encode_batch_device(self.ctx, C.c_void_p(items_dev), n, C.byref(scan), C.c_void_p(out_dev),
+                                                             C.c_size_t(out_stride), C.c_void_p(sizes_dev)), "mjx_huffman_encode_batch_device")
+
+
+class HuffTable(C.Structure):
+    _fields_ = [("bits", C.c_uint8 * 17), ("vals", C.c_uint8 * 256)]
+
+
+class Scan(C.Structure):
+    """mjx_scan_t"""
+    _fields_ = [("ncomp", C.c_int32), ("h_samp", C.c_int32 * MAX_COMPONENTS), ("v_samp", C.c_int32 * MAX_COMPONENTS),
+                ("dc_tbl", C.c_int32 * MAX_COMPONENTS), ("ac_tbl", C.c_int32 * MAX_COMPONENTS), ("mcus_per_row", C.c_int32),
+                ("mcu_rows", C.c_int32), ("dc", HuffTable * 4), ("ac", HuffTable * 4)]
+
+
+# The typical Huffman tables of ITU-T T.81 Annex K.3 (tables K.3 - K.6): what libjpeg installs for a compressor that is not
+# asked to optimise (jpeg_set_defaults -> std_huff_tables), i.e. what the reference's mj_write_jpeg_to_memory writes.
+STD_DC_LUMA = ([0, 1, 5, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0, 0, 0], list(range(12)))
+STD_DC_CHROMA = ([0, 3, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 0], list(range(12)))
+STD_AC_LUMA = ([0, 2, 1, 3, 3, 2, 4, 3, 5, 5, 4, 4, 0, 0, 1, 0x7d],
+               [0x01, 0x02, 0x03, 0x00, 0x04, 0x11, 0x05, 0x12, 0x21, 0x31, 0x41, 0x06, 0x13, 0x51, 0x61, 0x07, 0x22, 0x71, 0x14, 0x32,
+                0x81, 0x91, 0xa1, 0x08, 0x23, 0x42, 0xb1, 0xc1, 0x15, 0x52, 0xd1, 0xf0, 0x24, 0x33, 0x62, 0x72, 0x82, 0x09, 0x0a, 0x16,
+                0x17, 0x18, 0x19, 0x1a, 0x25, 0x26, 0x27, 0x28, 0x29, 0x2a, 0x34, 0x35, 0x36, 0x37, 0x38, 0x39, 0x3a, 0x43, 0x44, 0x45,
+                0x46, 0x47, 0x48, 0x49, 0x4a, 0x53, 0x54, 0x55, 0x56, 0x57, 0x58, 0x59, 0x5a, 0x63, 0x64, 0x65, 0x66, 0x67, 0x68, 0x69,
+                0x6a, 0x73, 0x74, 0x75, 0x76, 0x77, 0x78, 0x79, 0x7a, 0x83, 0x84, 0x85, 0x86, 0x87, 0x88, 0x89, 0x8a, 0x92, 0x93, 0x94,
+                0x95, 0x96, 0x97, 0x98, 0x99, 0x9a, 0xa2, 0xa3, 0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb2, 0xb3, 0xb4, 0xb5, 0xb6,
+                0xb7, 0xb8, 0xb9, 0xba, 0xc2, 0xc3, 0xc4, 0xc5, 0xc6, 0xc7, 0xc8, 0xc9, 0xca, 0xd2, 0xd3, 0xd4, 0xd5, 0xd6, 0xd7, 0xd8,
+                0xd9, 0xda, 0xe1, 0xe2, 0xe3, 0xe4, 0xe5, 0xe6, 0xe7, 0xe8, 0xe9, 0xea, 0xf1, 0xf2, 0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8,
+                0xf9, 0xfa])
+STD_AC_CHROMA = ([0, 2, 1, 2, 4, 4, 3, 4, 7, 5, 4, 4, 0, 1, 2, 0x77],
+                 [0x00, 0x01, 0x02, 0x03, 0x11, 0x04, 0x05, 0x21, 0x31, 0x06, 0x12, 0x41, 0x51, 0x07, 0x61, 0x71, 0x13, 0x22, 0x32, 0x81,
+                  0x08, 0x14, 0x42, 0x91, 0xa1, 0xb1, 0xc1, 0x09, 0x23, 0x33, 0x52, 0xf0, 0x15, 0x62, 0x72, 0xd1, 0x0a, 0x16, 0x24, 0x34,
+                  0xe1, 0x25, 0xf1, 0x17, 0x18, 0x19, 0x1a, 0x26, 0x27, 0x28, 0x29, 0x2a, 0x35, 0x36, 0x37, 0x38, 0x39, 0x3a, 0x43, 0x44,
+                  0x45, 0x46, 0x47, 0x48, 0x49, 0x4a, 0x53, 0x54, 0x55, 0x56, 0x57, 0x58, 0x59, 0x5a, 0x63, 0x64, 0x65, 0x66, 0x67, 0x68,
+                  0x69, 0x6a, 0x73, 0x74, 0x75, 0x76, 0x77, 0x78, 0x79, 0x7a, 0x82, 0x83, 0x84, 0x85, 0x86, 0x87, 0x88, 0x89, 0x8a, 0x92,
+                  0x93, 0x94, 0x95, 0x96, 0x97, 0x98, 0x99, 0x9a, 0xa2, 0xa3, 0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9, 0xaa, 0xb2, 0xb3, 0xb4,
+                  0xb5, 0xb6, 0xb7, 0xb8, 0xb9, 0xba, 0xc2, 0xc3, 0xc4, 0xc5, 0xc6, 0xc7, 0xc8, 0xc9, 0xca, 0xd2, 0xd3, 0xd4, 0xd5, 0xd6,
+                  0xd7, 0xd8, 0xd9, 0xda, 0xe2, 0xe3, 0xe4, 0xe5, 0xe6, 0xe7, 0xe8, 0xe9, 0xea, 0xf2, 0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8,
+                  0xf9, 0xfa])
+
+
+def _fill_table(t: HuffTable, spec) -> None:
+    counts, vals = spec
+    for k, cnt in enumerate(counts):
+        t.bits[k + 1] = cnt
+    for k, v in enumerate(vals):
+        t.vals[k] = v
+
+
+def standard_scan(width: int, height: int, samp: list[tuple[int, int]], chroma_from: int = 1) -> Scan:
+    """the scan libjpeg writes for an image of this size and sampling with its default (Annex K) tables: component 0 uses
+    tables 0 (luminance), components from `chroma_from` on tables 1 (jcparam.c jpeg_set_colorspace, YCbCr / grayscale)"""
+    s = Scan()
+    s.ncomp = len(samp)
+    max_h, max_v = max(h for h, _ in samp), max(v for _, v in samp)
+    for c, (h, v) in enumerate(samp):
+        s.h_samp[c], s.v_samp[c] = h, v
+        s.dc_tbl[c] = s.ac_tbl[c] = 1 if c >= chroma_from else 0
+    if len(samp) == 1:  # not interleaved: the component's own block grid
+        s.mcus_per_row, s.mcu_rows = (width + 7) // 8, (height + 7) // 8
+    else:
+        s.mcus_per_row, s.mcu_rows = -(-width // (8 * max_h)), -(-height // (8 * max_v))
+    _fill_table(s.dc[0], STD_DC_LUMA)
+    _fill_table(s.ac[0], STD_AC_LUMA)
+    _fill_table(s.dc[1], STD_DC_CHROMA)
+    _fill_table(s.ac[1], STD_AC_CHROMA)
+    return s
+
 
 def make_host_image(planes: list[np.ndarray], qtables: list[np.ndarray], real_dims=None):
     """HostImage over flat numpy planes; returns (struct, keepalive)."""
@@ -439,6 +511,7 @@ def load_modjpeg() -> C.CDLL:
     L.mj_read_jpeg_from_memory.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_size_t]
     L.mj_read_jpeg_from_file.argtypes = [vp, C.c_char_p, C.c_size_t]
     L.mj_write_jpeg_to_memory.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.c_int]
+    L.mjx_write_jpeg_to_memory_device.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.c_int]
     L.mj_write_jpeg_to_file.argtypes = [vp, C.c_char_p, C.c_int]
     L.mj_init_dropon.argtypes = [vp]
     L.mj_init_dropon.restype = None
@@ -497,6 +570,16 @@ class Jpeg:
     def write_jpeg_to_memory(self, options: int = 0) -> tuple[int, bytes]:
         mem, n = C.c_void_p(), C.c_size_t()
         rv = self.lib.mj_write_jpeg_to_memory(self.ptr, C.byref(mem), C.byref(n), options)
+        if rv != OK:
+            return rv, b""
+        out = C.string_at(mem, n.value)
+        _libc.free(mem)
+        return rv, out
+
+    def write_jpeg_to_memory_device(self, options: int = 0) -> tuple[int, bytes]:
+        """the same file with the scan Huffman-coded on the GPU (K4); baseline only"""
+        mem, n = C.c_void_p(), C.c_size_t()
+        rv = self.lib.mjx_write_jpeg_to_memory_device(self.ptr, C.byref(mem), C.byref(n), options)
         if rv != OK:
             return rv, b""
         out = C.string_at(mem, n.value)

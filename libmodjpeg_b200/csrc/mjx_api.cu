@@ -131,6 +131,7 @@ void mjx_ctx_destroy(mjx_ctx *ctx) {
     if(ctx->dev) cudaFree(ctx->dev);
     if(ctx->desc_dev) cudaFree(ctx->desc_dev);
     if(ctx->scratch) cudaFree(ctx->scratch);
+    if(ctx->huff) cudaFree(ctx->huff);
     if(ctx->side_stream) {
         cudaStreamSynchronize(ctx->side_stream);
         cudaStreamDestroy(ctx->side_stream);
