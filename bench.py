@@ -612,6 +612,36 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
         other["k3_effects_pixelate"] = {"ms": ms, "blocks": dc_blocks, "algorithmic_bytes": dc_blocks * 130,
                                         "achieved_gbs": dc_blocks * 130 / (ms * 1e-3) / 1e9, "gblocks_per_s": dc_blocks / (ms * 1e-3) / 1e9}
 
+        # K4: Huffman coding of every image of the batch on the device (the entropy encoder behind mj_write_jpeg_to_memory,
+        # reference src/image.c:194): coefficient planes resident in HBM -> entropy-coded segments in HBM
+        try:
+            scan = capi.standard_scan(info["width"], info["height"], samp)
+            cap = 1 << 20
+            seg = torch.empty((n, cap), dtype=torch.uint8, device=dev)
+            sizes = torch.zeros(n, dtype=torch.int32, device=dev)
+            ms = timed(lambda: engine.huffman_encode_batch_device(descs_dev.data_ptr(), n, scan, seg.data_ptr(), cap, sizes.data_ptr()), 3)
+            sz = sizes.cpu().numpy().view(np.uint32)
+            coded = int((sz != 0xFFFFFFFF).sum())
+            out_bytes = int(sz[sz != 0xFFFFFFFF].astype(np.int64).sum())
+            in_bytes = n * image_bytes
+            # the same encoder on the host: libjpeg's jpeg_write_coefficients through the library's host path, all host threads
+            hj = M.Jpeg()
+            assert hj.read_jpeg_from_memory(jpegs[0]) == 0
+            t_h = time.perf_counter()
+            reps_h = 8
+            for _ in range(reps_h):
+                assert hj.write_jpeg_to_memory(0)[0] == 0
+            host_ms = 1e3 * (time.perf_counter() - t_h) / reps_h
+            other["k4_huffman_encode"] = {"ms": ms, "images": n, "coded": coded, "images_per_s": n / (ms * 1e-3), "bytes_in": in_bytes, "bytes_out": out_bytes,
+                                          "algorithmic_bytes": in_bytes + out_bytes, "achieved_gbs": (in_bytes + out_bytes) / (ms * 1e-3) / 1e9,
+                                          "host_libjpeg_ms_per_image_1_thread": host_ms,
+                                          "note": "six launches (bit count, scan, emit, 0xFF count, scan, byte stuffing); the planes are read twice, "
+                                                  "algorithmic bytes count them once; host figure: mj_write_jpeg_to_memory of one such image on one core "
+                                                  "(markers + libjpeg's encode_mcu_huff), the encoder the reference uses"}
+            del seg
+        except Exception as e:  # noqa: BLE001
+            other["k4_huffman_encode"] = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+
     # ---- parity of the timed path against the unmodified reference (rank 0, outside every timed region) ----
     parity = None
     if rank == 0 and not args.no_parity:
@@ -738,8 +768,11 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
         if rank == 0:
             files = {"images": args.file_images * world, "threads_per_rank": threads, "ranks": world, "images_per_s": args.file_images * world / tf,
                      "mblocks_per_s": args.file_images * world * blocks_per_image / tf / 1e6,
-                     "path": "mj_compose_batch per rank: libjpeg entropy decode (thread pool) -> K1 once -> K2 one launch per window, zero-copy "
-                             "on a page-locked slab -> libjpeg entropy encode (thread pool); JPEG bytes in, JPEG bytes out",
+                     "path": ("mj_compose_batch per rank: libjpeg entropy decode (thread pool) -> K1 once -> whole planes of a window to HBM -> K2 -> "
+                              "K4 Huffman coding on the device -> entropy-coded segments back, libjpeg's markers in front (thread pool); "
+                              "JPEG bytes in, JPEG bytes out" if os.environ.get("MJX_GPU_HUFFMAN", "") != "0" else
+                              "mj_compose_batch per rank: libjpeg entropy decode (thread pool) -> K1 once -> K2 one launch per window, zero-copy "
+                              "on a page-locked slab -> libjpeg entropy encode (thread pool); JPEG bytes in, JPEG bytes out (MJX_GPU_HUFFMAN=0)"),
                      "bytes_in": sum(len(b) for b in batch) * world, "bytes_out": sum(len(o) for o in outs) * world}
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             try:

@@ -8,7 +8,10 @@
  *     blend            K2, ONE launch per window of images, working in place on a page-locked slab that holds the
  *                      region under the dropon of every image of the window (zero-copy over PCIe, mjx_compose_batch_host)
  *     entropy encode   host libjpeg, the same pool
- * Entropy coding is serial per image and stays on the CPU (north_star); the pool is what scales it.
+ * Entropy DEcoding is serial per image and stays on the CPU (north_star); the pool is what scales it.  For plain baseline
+ * output (write_options == 0; MJX_GPU_HUFFMAN=0 switches it off) the second half runs on the device instead
+ * (group_on_device): the window's whole planes go up once, K2 blends them in HBM, K4 (k4_huffman.cu) codes the scans, and
+ * only the entropy-coded segments -- a twentieth of the planes -- come back; the pool puts libjpeg's markers in front.
  */
 #include <pthread.h>
 #include <stdio.h>
@@ -38,7 +41,12 @@ typedef struct {
     int             ncomp;
     mjx_geometry_t  g;
     int             write_options;
-    double          phase_s[5]; /* MJ_BATCH_TRACE=1: seconds per phase ([0] = K2) */
+    double          phase_s[7]; /* MJ_BATCH_TRACE=1: seconds per phase ([0] = K2) */
+    /* phases 5 / 6: whole planes to the device, files from device-coded segments (MJX_GPU_HUFFMAN=1) */
+    size_t          image_bytes, plane_off[MJX_MAX_COMPONENTS];
+    int             stride[MJX_MAX_COMPONENTS], hreal[MJX_MAX_COMPONENTS], wreal[MJX_MAX_COMPONENTS];
+    const unsigned int *seg_size; /* per slot: bytes of the segment in the slot's slab region, 0xFFFFFFFF: not coded */
+    char           *written;      /* per window image: the output file exists already */
 } batch_t;
 
 static int take(batch_t *b, int limit) {
@@ -64,6 +72,29 @@ static int stage_rows(batch_t *b, int slot, mj_jpeg_t *m, int to_slab) {
         for(int l = 0; l < b->hb[c]; l++) {
             JBLOCKARRAY ba = (*m->cinfo.mem->access_virt_barray)((j_common_ptr)&m->cinfo, m->coef[c], y0 + (unsigned)l, 1, TRUE);
             char       *row = (char *)&ba[0][x0][0], *st = region + b->comp_off[c] + (size_t)l * wbytes;
+            if(to_slab) memcpy(st, row, wbytes);
+            else memcpy(row, st, wbytes);
+        }
+    }
+    trap->armed = 0;
+    return MJ_OK;
+}
+
+/* copy every real row of every plane between libjpeg's arrays and the image's slab region (whole image, not only the region
+ * under the dropon: the device also codes the file, k4_huffman.cu) */
+static int stage_planes(batch_t *b, int slot, mj_jpeg_t *m, int to_slab) {
+    mjp_trap_t *trap = mjp_image_trap(m);
+    trap->armed = 1;
+    if(setjmp(trap->escape)) {
+        trap->armed = 0;
+        return MJ_ERR_DECODE_JPEG;
+    }
+    char *region = b->slab + (size_t)slot * b->image_bytes;
+    for(int c = 0; c < b->ncomp; c++) {
+        const size_t wbytes = (size_t)b->stride[c] * 128;
+        for(int l = 0; l < b->hreal[c]; l++) {
+            JBLOCKARRAY ba = (*m->cinfo.mem->access_virt_barray)((j_common_ptr)&m->cinfo, m->coef[c], (unsigned)l, 1, TRUE);
+            char       *row = (char *)&ba[0][0][0], *st = region + b->plane_off[c] + (size_t)l * wbytes;
             if(to_slab) memcpy(st, row, wbytes);
             else memcpy(row, st, wbytes);
         }
@@ -98,11 +129,33 @@ static void *worker(void *arg) {
                 if(rv != MJ_OK) b->status[i] = rv;
             }
         }
+        else if(b->phase == 5) { /* whole planes -> page-locked slab */
+            int s = take(b, b->ngroup);
+            if(s < 0) break;
+            const int i = b->group[s];
+            int       rv = stage_planes(b, s, &b->jp[i - b->w0], 1);
+            if(rv != MJ_OK) b->status[i] = rv;
+        }
+        else if(b->phase == 6) { /* the file: libjpeg's markers + the segment the device coded + EOI */
+            int s = take(b, b->ngroup);
+            if(s < 0) break;
+            const int i = b->group[s];
+            if(b->status[i] != MJ_OK || b->seg_size[s] == 0xFFFFFFFFu) continue;
+            unsigned char *head = NULL;
+            size_t         head_len = 0;
+            mjx_scan_t     scan;
+            int            rv = mjp_scan_headers(&b->jp[i - b->w0], &head, &head_len, &scan);
+            if(rv == MJ_OK) rv = mjp_assemble_file(&b->out[i].data, &b->out[i].len, head, head_len, (const unsigned char *)b->slab + (size_t)s * b->image_bytes, b->seg_size[s]);
+            free(head);
+            if(rv == MJ_OK) b->written[i - b->w0] = 1;
+            else b->status[i] = rv;
+        }
         else { /* 4: encode + free, every image of the window */
             int k = take(b, b->w1 - b->w0);
             if(k < 0) break;
             const int i = b->w0 + k;
-            if(b->status[i] == MJ_OK) b->status[i] = mj_write_jpeg_to_memory(&b->jp[k], &b->out[i].data, &b->out[i].len, b->write_options);
+            if(b->status[i] == MJ_OK && !(b->written && b->written[k]))
+                b->status[i] = mj_write_jpeg_to_memory(&b->jp[k], &b->out[i].data, &b->out[i].len, b->write_options);
             mj_free_jpeg(&b->jp[k]);
         }
     }
@@ -140,6 +193,118 @@ static int same_geometry(const mj_jpeg_t *a, const mj_jpeg_t *b) {
     return 1;
 }
 
+/* Device buffers of the device-resident path, kept across groups and windows */
+typedef struct {
+    void  *planes, *segs, *sizes, *descs;
+    size_t planes_bytes, segs_bytes, sizes_bytes, descs_bytes;
+} devbufs_t;
+
+static int dev_grow(mjx_ctx *ctx, void **p, size_t *have, size_t want) {
+    if(*have >= want) return MJX_OK;
+    if(*p) mjx_device_free(ctx, *p);
+    *p = NULL;
+    *have = 0;
+    int rv = mjx_device_alloc(ctx, p, want + want / 8);
+    if(rv == MJX_OK) *have = want + want / 8;
+    return rv;
+}
+
+static void dev_release(mjx_ctx *ctx, devbufs_t *v) {
+    if(v->planes) mjx_device_free(ctx, v->planes);
+    if(v->segs) mjx_device_free(ctx, v->segs);
+    if(v->sizes) mjx_device_free(ctx, v->sizes);
+    if(v->descs) mjx_device_free(ctx, v->descs);
+    memset(v, 0, sizeof(*v));
+}
+
+/* One group (images of one geometry) entirely on the device: whole planes up, K2 in HBM, K4 codes the scans, only the
+ * entropy-coded segments come back; the workers put libjpeg's markers in front of them.  Images the device cannot code
+ * (a coefficient outside the baseline tables, a segment beyond the slab) get their planes back and are left to libjpeg.
+ * Returns MJ_OK when the group was handled (per-image results in status / written), another code when nothing was done and
+ * the ordinary path should take the group. */
+static int group_on_device(batch_t *b, mjx_ctx *ctx, devbufs_t *v, mjx_dropon *cd, int nthreads, pthread_t *th, unsigned int *seg_size) {
+    mj_jpeg_t *ref = &b->jp[b->group[0] - b->w0];
+    mjx_scan_t scan;
+    {
+        unsigned char *head = NULL;
+        size_t         head_len = 0;
+        const int      rv = mjp_scan_headers(ref, &head, &head_len, &scan);
+        free(head);
+        if(rv != MJ_OK) return rv;
+    }
+    b->image_bytes = 0;
+    for(int c = 0; c < b->ncomp; c++) {
+        const jpeg_component_info *ci = &ref->cinfo.comp_info[c];
+        b->stride[c] = (int)mjp_virtual_width(ci);
+        b->wreal[c] = (int)ci->width_in_blocks;
+        b->hreal[c] = (int)ci->height_in_blocks;
+        b->plane_off[c] = b->image_bytes;
+        b->image_bytes += ((size_t)b->stride[c] * (size_t)b->hreal[c] * 128 + 255) & ~(size_t)255;
+    }
+    /* a segment as long as a quarter of the coefficients is a file of ~4 bits per coefficient: beyond what quality 100 produces */
+    size_t cap = (b->image_bytes / 4 + 255) & ~(size_t)255;
+    if(cap < 65536) cap = 65536;
+    if(cap > b->image_bytes) cap = b->image_bytes;
+    const size_t ng = (size_t)b->ngroup;
+    void        *slab = NULL;
+    int          rv = mjx_ctx_pinned_scratch(ctx, b->image_bytes * ng + sizeof(mjx_image_desc_t) * ng, &slab);
+    if(rv == MJX_OK) rv = dev_grow(ctx, &v->planes, &v->planes_bytes, b->image_bytes * ng);
+    if(rv == MJX_OK) rv = dev_grow(ctx, &v->segs, &v->segs_bytes, cap * ng);
+    if(rv == MJX_OK) rv = dev_grow(ctx, &v->sizes, &v->sizes_bytes, 4 * ng);
+    if(rv == MJX_OK) rv = dev_grow(ctx, &v->descs, &v->descs_bytes, sizeof(mjx_image_desc_t) * ng);
+    if(rv != MJX_OK) return mjp_map_error(rv);
+    b->slab = (char *)slab;
+    run_phase(b, 5, nthreads, th); /* whole planes -> page-locked slab */
+
+    mjx_image_desc_t *descs = (mjx_image_desc_t *)(b->slab + b->image_bytes * ng);
+    memset(descs, 0, sizeof(mjx_image_desc_t) * ng);
+    for(int s = 0; s < b->ngroup; s++) {
+        mj_jpeg_t *m = &b->jp[b->group[s] - b->w0];
+        for(int c = 0; c < b->ncomp; c++) {
+            descs[s].plane[c] = (uint64_t)(uintptr_t)((char *)v->planes + (size_t)s * b->image_bytes + b->plane_off[c]);
+            descs[s].stride_blocks[c] = b->stride[c];
+            descs[s].rows[c] = b->hreal[c];
+            descs[s].wreal[c] = b->wreal[c];
+            descs[s].hreal[c] = b->hreal[c];
+            const JQUANT_TBL *qt = m->cinfo.comp_info[c].quant_table;
+            if(qt == NULL) b->status[b->group[s]] = MJ_ERR_NULL_DATA;
+            else memcpy(descs[s].q[c], qt->quantval, 128);
+        }
+    }
+    for(int s = 0; s < b->ngroup; s++)
+        if(b->status[b->group[s]] != MJ_OK) return MJ_ERR_NULL_DATA; /* (the caller marks the group) */
+
+    const double tk = now_s();
+    rv = mjx_copy_h2d(ctx, v->planes, b->slab, b->image_bytes * ng);
+    if(rv == MJX_OK) rv = mjx_copy_h2d(ctx, v->descs, descs, sizeof(mjx_image_desc_t) * ng);
+    if(rv == MJX_OK) rv = mjx_compose_batch_device(ctx, (const mjx_image_desc_t *)v->descs, b->ngroup, cd, b->g.block_x, b->g.block_y);
+    if(rv == MJX_OK) rv = mjx_huffman_encode_batch_device(ctx, (const mjx_image_desc_t *)v->descs, b->ngroup, &scan, v->segs, cap, (uint32_t *)v->sizes);
+    if(rv == MJX_OK) rv = mjx_copy_d2h(ctx, seg_size, v->sizes, 4 * ng);
+    if(rv == MJX_OK) rv = mjx_ctx_sync(ctx);
+    /* the segments, each at the start of its image's slab region (the planes there have been uploaded); an image that was not
+     * coded gets its composed planes back instead */
+    for(int s = 0; rv == MJX_OK && s < b->ngroup; s++) {
+        if(seg_size[s] != 0xFFFFFFFFu) rv = mjx_copy_d2h(ctx, b->slab + (size_t)s * b->image_bytes, (char *)v->segs + (size_t)s * cap, seg_size[s]);
+        else rv = mjx_copy_d2h(ctx, b->slab + (size_t)s * b->image_bytes, (char *)v->planes + (size_t)s * b->image_bytes, b->image_bytes);
+    }
+    if(rv == MJX_OK) rv = mjx_ctx_sync(ctx);
+    b->phase_s[0] += now_s() - tk;
+    if(rv != MJX_OK) {
+        fprintf(stderr, "libmodjpeg (B200): device batch failed: %s\n", mjx_ctx_last_error(ctx));
+        return mjp_map_error(rv);
+    }
+    b->seg_size = seg_size;
+    run_phase(b, 6, nthreads, th); /* files */
+    for(int s = 0; s < b->ngroup; s++) { /* not coded on the device: composed planes back into libjpeg's arrays, phase 4 encodes */
+        const int i = b->group[s];
+        if(seg_size[s] == 0xFFFFFFFFu && b->status[i] == MJ_OK) {
+            const int r2 = stage_planes(b, s, &b->jp[i - b->w0], 0);
+            if(r2 != MJ_OK) b->status[i] = r2;
+        }
+    }
+    return MJ_OK;
+}
+
 /* the pipeline on the calling thread's device */
 static int batch_on_device(int n, const mj_blob_t *in, mj_blob_t *out, int *status, mj_dropon_t *d, unsigned int align, int offset_x,
                            int offset_y, int write_options, int nthreads) {
@@ -157,6 +322,12 @@ static int batch_on_device(int n, const mj_blob_t *in, mj_blob_t *out, int *stat
     b.jp = (mj_jpeg_t *)calloc((size_t)window, sizeof(mj_jpeg_t));
     int       *group = (int *)malloc(sizeof(int) * (size_t)window);
     char      *done = (char *)malloc((size_t)window);
+    /* a plain baseline file wanted (and MJX_GPU_HUFFMAN not 0): planes, blend and entropy coding of a group stay on the device */
+    const int     on_device = compose && write_options == 0 && mjp_gpu_huffman_mode() != 0;
+    unsigned int *seg_size = (unsigned int *)malloc(sizeof(unsigned int) * (size_t)window);
+    devbufs_t     dv;
+    memset(&dv, 0, sizeof(dv));
+    b.written = (char *)calloc((size_t)window, 1);
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
     mjx_host_image_t *items = (mjx_host_image_t *)malloc(sizeof(mjx_host_image_t) * (size_t)window);
     int            result = MJ_OK;
@@ -165,7 +336,7 @@ static int batch_on_device(int n, const mj_blob_t *in, mj_blob_t *out, int *stat
     mjx_geometry_t cd_g;
     memset(&cd_layout, 0, sizeof(cd_layout));
     memset(&cd_g, 0, sizeof(cd_g));
-    if(b.jp == NULL || group == NULL || done == NULL || th == NULL || items == NULL) {
+    if(b.jp == NULL || group == NULL || done == NULL || th == NULL || items == NULL || seg_size == NULL || b.written == NULL) {
         result = MJ_ERR_MEMORY;
         goto out;
     }
@@ -176,6 +347,7 @@ static int batch_on_device(int n, const mj_blob_t *in, mj_blob_t *out, int *stat
 
         /* compose the window group by group (images sharing one geometry share one compiled dropon and one launch) */
         memset(done, 0, (size_t)window);
+        memset(b.written, 0, (size_t)window);
         for(int k0 = 0; compose && k0 < b.w1 - b.w0; k0++) {
             if(done[k0] || status[b.w0 + k0] != MJ_OK) continue;
             mj_jpeg_t *ref = &b.jp[k0];
@@ -202,6 +374,15 @@ static int batch_on_device(int n, const mj_blob_t *in, mj_blob_t *out, int *stat
                                         b.g.blockoffset_y, b.g.crop_x, b.g.crop_y, b.g.crop_w, b.g.crop_h, 0);
                 if(rv == MJX_ERR_UNSUPPORTED) fprintf(stderr, "Unsupported color conversion request\n");
                 rv = mjp_map_error(rv);
+            }
+            if(rv == MJ_OK && on_device) {
+                b.ncomp = layout.ncomp;
+                b.group = group;
+                if(group_on_device(&b, ctx, &dv, cd, nthreads, th, seg_size) == MJ_OK) continue;
+                /* (not a file the device codes, or no memory for it: the ordinary path below) */
+                int bad = 0;
+                for(int s = 0; s < b.ngroup; s++) bad |= status[group[s]] != MJ_OK;
+                if(bad) rv = MJ_ERR_NULL_DATA;
             }
             if(rv == MJ_OK) {
                 b.ncomp = layout.ncomp;
@@ -248,9 +429,13 @@ static int batch_on_device(int n, const mj_blob_t *in, mj_blob_t *out, int *stat
         run_phase(&b, 4, nthreads, th); /* entropy encode + free */
     }
     if(getenv("MJ_BATCH_TRACE") != NULL)
-        fprintf(stderr, "mj_compose_batch: %d images, %d threads: decode %.3f s, stage-in %.3f s, K2 %.3f s, stage-out %.3f s, encode %.3f s\n", n,
-                nthreads, b.phase_s[1], b.phase_s[2], b.phase_s[0], b.phase_s[3], b.phase_s[4]);
+        fprintf(stderr, "mj_compose_batch: %d images, %d threads: decode %.3f s, stage-in %.3f s, K2%s %.3f s, stage-out %.3f s, %s %.3f s\n", n,
+                nthreads, b.phase_s[1], b.phase_s[2] + b.phase_s[5], on_device ? " + copies + K4" : "", b.phase_s[0], b.phase_s[3],
+                on_device ? "files (markers + segment) + host encode" : "encode", b.phase_s[4] + b.phase_s[6]);
 out:
+    if(ctx != NULL) dev_release(ctx, &dv);
+    free(seg_size);
+    free(b.written);
     if(cd != NULL) mjx_dropon_free(cd);
     free(b.jp);
     free(group);

@@ -122,21 +122,19 @@ static void copy_table(mjx_huff_table_t *dst, const JHUFF_TBL *src) {
     memcpy(dst->vals, src->huffval, 256);
 }
 
-int mjx_write_jpeg_to_memory_device(mj_jpeg_t *m, unsigned char **memory, size_t *len, int options) {
-    if(m == NULL || memory == NULL || len == NULL || m->coef == NULL) return MJ_ERR_NULL_DATA;
-    if(options & (MJ_OPTION_OPTIMIZE | MJ_OPTION_PROGRESSIVE | MJ_OPTION_ARITHMETRIC)) return MJ_ERR_UNSUPPORTED_FILETYPE;
+/* Everything of the output file in front of the entropy-coded segment (SOI ... SOS header), written by libjpeg itself, and the
+ * description of the one scan that follows it.  MJ_ERR_UNSUPPORTED_FILETYPE: not a file the device encoder takes. */
+int mjp_scan_headers(mj_jpeg_t *m, unsigned char **head, size_t *head_len, mjx_scan_t *scan) {
+    *head = NULL;
+    *head_len = 0;
     const int nc = m->cinfo.num_components;
     if(nc < 1 || nc > MJX_MAX_COMPONENTS || m->cinfo.data_precision != 8) return MJ_ERR_UNSUPPORTED_FILETYPE;
-    mjx_ctx *ctx = mjx_host_ctx();
-    if(ctx == NULL) return MJ_ERR_DEVICE;
 
     struct jpeg_compress_struct out;
     mjp_trap_t                  trap;
     mjp_memdst_t                dst;
     mjp_stop_t                  stop;
     mjp_trap_t                 *itrap = mjp_image_trap(m);
-    unsigned char *volatile     scan_bytes = NULL;
-    short **volatile            rowbuf = NULL;
     volatile int                rv = MJ_ERR_ENCODE_JPEG;
 
     memset(&out, 0, sizeof(out)); /* jpeg_destroy_compress accepts it at any point below */
@@ -158,18 +156,17 @@ int mjx_write_jpeg_to_memory_device(mj_jpeg_t *m, unsigned char **memory, size_t
         goto done;
     }
 
-    /* the scan libjpeg is about to describe in SOS: every component, its tables, the MCU grid */
-    mjx_scan_t scan;
-    memset(&scan, 0, sizeof(scan));
-    scan.ncomp = nc;
+    /* the scan libjpeg is about to describe in SOS: every component, its tables, the MCU grid (jcmaster.c per_scan_setup) */
+    memset(scan, 0, sizeof(*scan));
+    scan->ncomp = nc;
     {
         int blocks = 0;
         for(int c = 0; c < nc; c++) {
             const jpeg_component_info *ci = &out.comp_info[c];
-            scan.h_samp[c] = ci->h_samp_factor;
-            scan.v_samp[c] = ci->v_samp_factor;
-            scan.dc_tbl[c] = ci->dc_tbl_no;
-            scan.ac_tbl[c] = ci->ac_tbl_no;
+            scan->h_samp[c] = ci->h_samp_factor;
+            scan->v_samp[c] = ci->v_samp_factor;
+            scan->dc_tbl[c] = ci->dc_tbl_no;
+            scan->ac_tbl[c] = ci->ac_tbl_no;
             blocks += ci->h_samp_factor * ci->v_samp_factor;
         }
         if(nc > 1 && blocks > 10) { /* C_MAX_BLOCKS_IN_MCU: libjpeg refuses the scan; let it say so */
@@ -177,8 +174,17 @@ int mjx_write_jpeg_to_memory_device(mj_jpeg_t *m, unsigned char **memory, size_t
             goto done;
         }
         for(int i = 0; i < 4; i++) {
-            copy_table(&scan.dc[i], out.dc_huff_tbl_ptrs[i]);
-            copy_table(&scan.ac[i], out.ac_huff_tbl_ptrs[i]);
+            copy_table(&scan->dc[i], out.dc_huff_tbl_ptrs[i]);
+            copy_table(&scan->ac[i], out.ac_huff_tbl_ptrs[i]);
+        }
+        if(nc == 1) {
+            scan->mcus_per_row = (int)m->cinfo.comp_info[0].width_in_blocks;
+            scan->mcu_rows = (int)m->cinfo.comp_info[0].height_in_blocks;
+        }
+        else {
+            const long mw = (long)m->cinfo.max_h_samp_factor * DCTSIZE, mh = (long)m->cinfo.max_v_samp_factor * DCTSIZE;
+            scan->mcus_per_row = (int)(((long)m->cinfo.image_width + mw - 1) / mw);
+            scan->mcu_rows = (int)(((long)m->cinfo.image_height + mh - 1) / mh);
         }
     }
 
@@ -192,85 +198,104 @@ int mjx_write_jpeg_to_memory_device(mj_jpeg_t *m, unsigned char **memory, size_t
         jpeg_finish_compress(&out); /* leaves through stop_after_headers once the headers are out */
         goto done;                  /* (not reached for an image with at least one row of blocks) */
     }
-    {
-        const size_t head = dst.capacity - dst.base.free_in_buffer;
-        /* geometry as libjpeg's per_scan_setup computes it (jcmaster.c) */
-        int    stride[MJX_MAX_COMPONENTS], vrows[MJX_MAX_COMPONENTS], wreal[MJX_MAX_COMPONENTS], hreal[MJX_MAX_COMPONENTS];
-        size_t nrows = 0;
-        for(int c = 0; c < nc; c++) {
-            const jpeg_component_info *ci = &m->cinfo.comp_info[c];
-            stride[c] = (int)mjp_virtual_width(ci);
-            vrows[c] = (int)mjp_virtual_height(ci);
-            wreal[c] = (int)ci->width_in_blocks;
-            hreal[c] = (int)ci->height_in_blocks;
-            nrows += (size_t)hreal[c];
-        }
-        if(nc == 1) {
-            scan.mcus_per_row = wreal[0];
-            scan.mcu_rows = hreal[0];
-        }
-        else {
-            const long mw = (long)m->cinfo.max_h_samp_factor * DCTSIZE, mh = (long)m->cinfo.max_v_samp_factor * DCTSIZE;
-            scan.mcus_per_row = (int)(((long)m->cinfo.image_width + mw - 1) / mw);
-            scan.mcu_rows = (int)(((long)m->cinfo.image_height + mh - 1) / mh);
-        }
-        rowbuf = (short **)malloc(nrows * sizeof(short *));
-        if(rowbuf == NULL) {
-            rv = MJ_ERR_MEMORY;
-            goto done;
-        }
-        const short *const *rows[MJX_MAX_COMPONENTS] = {NULL, NULL, NULL, NULL};
-        size_t              at = 0;
-        for(int c = 0; c < nc; c++) {
-            rows[c] = (const short *const *)(rowbuf + at);
-            for(int l = 0; l < hreal[c]; l++) {
-                JBLOCKARRAY ba = (*m->cinfo.mem->access_virt_barray)((j_common_ptr)&m->cinfo, m->coef[c], (JDIMENSION)l, 1, FALSE);
-                rowbuf[at++] = (short *)ba[0];
-            }
-        }
-        unsigned char *sb = NULL;
-        size_t         sl = 0;
-        const int      mrv = mjx_huffman_encode_rows_host(ctx, nc, rows, stride, vrows, wreal, hreal, &scan, &sb, &sl);
-        scan_bytes = sb;
-        if(mrv != MJX_OK) {
-            rv = mrv == MJX_ERR_UNSUPPORTED ? MJ_ERR_UNSUPPORTED_FILETYPE : mjp_map_error(mrv);
-            goto done;
-        }
-        unsigned char *file = (unsigned char *)malloc(head + sl + 2);
-        if(file == NULL) {
-            rv = MJ_ERR_MEMORY;
-            goto done;
-        }
-        memcpy(file, dst.data, head);
-        memcpy(file + head, sb, sl);
-        file[head + sl] = 0xFF;
-        file[head + sl + 1] = 0xD9; /* EOI */
-        *memory = file;
-        *len = head + sl + 2;
-        rv = MJ_OK;
-    }
+    *head_len = dst.capacity - dst.base.free_in_buffer;
+    *head = dst.data; /* handed to the caller */
+    dst.data = NULL;
+    rv = MJ_OK;
 done:
     jpeg_destroy_compress(&out);
     free(dst.data);
-    free(scan_bytes);
-    free((void *)rowbuf);
     itrap->armed = 0;
     return rv;
 }
 
-/* MJX_GPU_HUFFMAN=1: mj_write_jpeg_to_memory codes baseline scans on the device */
-static int gpu_huffman_enabled(void) {
-    static int state = -1;
-    if(state < 0) {
+int mjx_write_jpeg_to_memory_device(mj_jpeg_t *m, unsigned char **memory, size_t *len, int options) {
+    if(m == NULL || memory == NULL || len == NULL || m->coef == NULL) return MJ_ERR_NULL_DATA;
+    if(options & (MJ_OPTION_OPTIMIZE | MJ_OPTION_PROGRESSIVE | MJ_OPTION_ARITHMETRIC)) return MJ_ERR_UNSUPPORTED_FILETYPE;
+    mjx_ctx *ctx = mjx_host_ctx();
+    if(ctx == NULL) return MJ_ERR_DEVICE;
+
+    unsigned char *head = NULL, *sb = NULL;
+    size_t         head_len = 0, sl = 0;
+    mjx_scan_t     scan;
+    int            rv = mjp_scan_headers(m, &head, &head_len, &scan);
+    if(rv != MJ_OK) return rv;
+
+    const int   nc = m->cinfo.num_components;
+    int         stride[MJX_MAX_COMPONENTS], vrows[MJX_MAX_COMPONENTS], wreal[MJX_MAX_COMPONENTS], hreal[MJX_MAX_COMPONENTS];
+    size_t      nrows = 0;
+    for(int c = 0; c < nc; c++) {
+        const jpeg_component_info *ci = &m->cinfo.comp_info[c];
+        stride[c] = (int)mjp_virtual_width(ci);
+        vrows[c] = (int)mjp_virtual_height(ci);
+        wreal[c] = (int)ci->width_in_blocks;
+        hreal[c] = (int)ci->height_in_blocks;
+        nrows += (size_t)hreal[c];
+    }
+    short **rowbuf = (short **)malloc(nrows * sizeof(short *));
+    if(rowbuf == NULL) {
+        free(head);
+        return MJ_ERR_MEMORY;
+    }
+    mjp_trap_t *itrap = mjp_image_trap(m);
+    itrap->armed = 1;
+    if(setjmp(itrap->escape)) {
+        itrap->armed = 0;
+        free(head);
+        free(rowbuf);
+        return MJ_ERR_ENCODE_JPEG;
+    }
+    const short *const *rows[MJX_MAX_COMPONENTS] = {NULL, NULL, NULL, NULL};
+    size_t              at = 0;
+    for(int c = 0; c < nc; c++) {
+        rows[c] = (const short *const *)(rowbuf + at);
+        for(int l = 0; l < hreal[c]; l++) {
+            JBLOCKARRAY ba = (*m->cinfo.mem->access_virt_barray)((j_common_ptr)&m->cinfo, m->coef[c], (JDIMENSION)l, 1, FALSE);
+            rowbuf[at++] = (short *)ba[0];
+        }
+    }
+    itrap->armed = 0;
+    const int mrv = mjx_huffman_encode_rows_host(ctx, nc, rows, stride, vrows, wreal, hreal, &scan, &sb, &sl);
+    free(rowbuf);
+    if(mrv != MJX_OK) {
+        free(head);
+        return mrv == MJX_ERR_UNSUPPORTED ? MJ_ERR_UNSUPPORTED_FILETYPE : mjp_map_error(mrv);
+    }
+    rv = mjp_assemble_file(memory, len, head, head_len, sb, sl);
+    free(head);
+    free(sb);
+    return rv;
+}
+
+/* header + entropy-coded segment + EOI */
+int mjp_assemble_file(unsigned char **memory, size_t *len, const unsigned char *head, size_t head_len, const unsigned char *seg, size_t seg_len) {
+    unsigned char *file = (unsigned char *)malloc(head_len + seg_len + 2);
+    if(file == NULL) return MJ_ERR_MEMORY;
+    memcpy(file, head, head_len);
+    memcpy(file + head_len, seg, seg_len);
+    file[head_len + seg_len] = 0xFF;
+    file[head_len + seg_len + 1] = 0xD9;
+    *memory = file;
+    *len = head_len + seg_len + 2;
+    return MJ_OK;
+}
+
+/* MJX_GPU_HUFFMAN: 1 = mj_write_jpeg_to_memory codes baseline scans on the device, and so does mj_compose_batch; 0 = nobody
+ * does; unset = mj_compose_batch does (whole windows of images stay in HBM between blend and entropy coding, which pays:
+ * 965 -> 1 280 files/s on the bench batch), single writes stay on the host (for one image the staging copy of its planes
+ * costs what libjpeg's encoder costs).  Returns -1 (unset), 0 or 1. */
+int mjp_gpu_huffman_mode(void) {
+    static int state = -2;
+    if(state == -2) {
         const char *e = getenv("MJX_GPU_HUFFMAN");
-        state = (e != NULL && *e && *e != '0') ? 1 : 0;
+        state = (e == NULL || !*e) ? -1 : (*e != '0' ? 1 : 0);
     }
     return state;
 }
 
 int mj_write_jpeg_to_memory(mj_jpeg_t *m, unsigned char **memory, size_t *len, int options) {
     if(m == NULL || memory == NULL || len == NULL || m->coef == NULL) return MJ_ERR_NULL_DATA;
-    if(gpu_huffman_enabled() && !(options & (MJ_OPTION_OPTIMIZE | MJ_OPTION_PROGRESSIVE | MJ_OPTION_ARITHMETRIC))) {
+    if(mjp_gpu_huffman_mode() == 1 && !(options & (MJ_OPTION_OPTIMIZE | MJ_OPTION_PROGRESSIVE | MJ_OPTION_ARITHMETRIC))) {
         /* anything the device path does not take (or cannot code) goes through libjpeg below, which also owns the error */
         if(mjx_write_jpeg_to_memory_device(m, memory, len, options) == MJ_OK) return MJ_OK;
     }

@@ -64,6 +64,12 @@ void mjp_compose_cache_clear(void);
 int mjp_coalesce_enabled(void);
 int mjp_coalesce_compose(mj_jpeg_t *m, mj_dropon_t *d, const mjx_layout_t *layout, const mjx_geometry_t *g, int *result);
 
+/* entropy coding on the device (mj_image.c): $MJX_GPU_HUFFMAN; the file in front of the entropy-coded segment as libjpeg writes
+ * it (malloc()ed) + the description of the scan; header + segment + EOI as one malloc()ed file */
+int mjp_gpu_huffman_mode(void); /* -1 unset, 0 off, 1 on */
+int mjp_scan_headers(mj_jpeg_t *m, unsigned char **head, size_t *head_len, mjx_scan_t *scan);
+int mjp_assemble_file(unsigned char **memory, size_t *len, const unsigned char *head, size_t head_len, const unsigned char *seg, size_t seg_len);
+
 /* MJX_* -> MJ_* */
 int mjp_map_error(int mjx_rv);
 

@@ -143,3 +143,34 @@ def test_write_path_env_switch(engine, tmp_path):
         subprocess.run([sys.executable, "-c", code % (root, os.path.dirname(os.path.abspath(__file__)), pa, pb)], check=True, env=env)
         outs[flag] = (open(pa, "rb").read(), open(pb, "rb").read())
     assert outs["0"] == outs["1"]
+
+
+def test_compose_batch_device_resident_pipeline(engine, tmp_path):
+    """mj_compose_batch with MJX_GPU_HUFFMAN=1: whole planes up, K2 + K4 in HBM, only the segments come back -- the files
+    equal the ones of the ordinary pipeline (host libjpeg encode), image by image; mixed geometries (4:2:0, 4:4:4 with an odd
+    size, grayscale smaller than the dropon) and an undecodable input in one batch"""
+    import pickle
+    import subprocess
+
+    code = (
+        "import sys, pickle; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np, libmodjpeg_b200 as M, util\n"
+        "from libmodjpeg_b200 import capi\n"
+        "d = M.Dropon(); assert d.read_dropon_from_raw(util.logo_rgba(200, 120, tile=64, radius=27), M.CS_RGBA, 255) == 0\n"
+        "jp = [util.jpeg_bytes(320, 240, '420', 85, seed=300 + i) for i in range(5)] + [util.jpeg_bytes(275, 203, '444', 90, seed=310 + i) for i in range(3)]\n"
+        "jp += [b'definitely not a jpeg', util.jpeg_bytes(320, 240, '420', 100, seed=77), util.jpeg_bytes(96, 64, '444', 85, seed=5, gray=True)]\n"
+        "order = [0, 5, 1, 8, 6, 2, 9, 3, 7, 10, 4]\n"
+        "rv, status, outs = capi.compose_batch([jp[i] for i in order], d, M.ALIGN_CENTER, 7, -5, 0, nthreads=4)\n"
+        "pickle.dump((rv, list(status), outs), open(%r, 'wb'))\n"
+    )
+    here = os.path.dirname(os.path.abspath(__file__))
+    res = {}
+    for flag in ("0", "1"):
+        path = str(tmp_path / f"r{flag}.pkl")
+        subprocess.run([sys.executable, "-c", code % (os.path.join(here, ".."), here, path)], check=True, env=dict(os.environ, MJX_GPU_HUFFMAN=flag))
+        res[flag] = pickle.load(open(path, "rb"))
+    assert res["0"][0] == 0 and res["1"][0] == 0
+    assert res["0"][1] == res["1"][1]
+    assert sum(1 for s in res["1"][1] if s == 0) == 10
+    for a, b in zip(res["0"][2], res["1"][2]):
+        assert a == b
