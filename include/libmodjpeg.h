@@ -78,6 +78,37 @@ enum { /* return codes */
     MJ_ERR_DEVICE /* 10, additive: no usable CUDA device, or a kernel launch failed */
 };
 
+/* The reference spells these constants as macros; callers that test them with #ifdef keep compiling the same way. */
+#define MJ_COLORSPACE_RGB MJ_COLORSPACE_RGB
+#define MJ_COLORSPACE_RGBA MJ_COLORSPACE_RGBA
+#define MJ_COLORSPACE_GRAYSCALE MJ_COLORSPACE_GRAYSCALE
+#define MJ_COLORSPACE_GRAYSCALEA MJ_COLORSPACE_GRAYSCALEA
+#define MJ_COLORSPACE_YCC MJ_COLORSPACE_YCC
+#define MJ_COLORSPACE_YCCA MJ_COLORSPACE_YCCA
+#define MJ_ALIGN_LEFT MJ_ALIGN_LEFT
+#define MJ_ALIGN_RIGHT MJ_ALIGN_RIGHT
+#define MJ_ALIGN_TOP MJ_ALIGN_TOP
+#define MJ_ALIGN_BOTTOM MJ_ALIGN_BOTTOM
+#define MJ_ALIGN_CENTER MJ_ALIGN_CENTER
+#define MJ_BLEND_NONUNIFORM MJ_BLEND_NONUNIFORM
+#define MJ_BLEND_NONE MJ_BLEND_NONE
+#define MJ_BLEND_FULL MJ_BLEND_FULL
+#define MJ_OPTION_NONE MJ_OPTION_NONE
+#define MJ_OPTION_OPTIMIZE MJ_OPTION_OPTIMIZE
+#define MJ_OPTION_PROGRESSIVE MJ_OPTION_PROGRESSIVE
+#define MJ_OPTION_ARITHMETRIC MJ_OPTION_ARITHMETRIC
+#define MJ_OK MJ_OK
+#define MJ_ERR_MEMORY MJ_ERR_MEMORY
+#define MJ_ERR_NULL_DATA MJ_ERR_NULL_DATA
+#define MJ_ERR_DROPON_DIMENSIONS MJ_ERR_DROPON_DIMENSIONS
+#define MJ_ERR_UNSUPPORTED_COLORSPACE MJ_ERR_UNSUPPORTED_COLORSPACE
+#define MJ_ERR_DECODE_JPEG MJ_ERR_DECODE_JPEG
+#define MJ_ERR_ENCODE_JPEG MJ_ERR_ENCODE_JPEG
+#define MJ_ERR_FILEIO MJ_ERR_FILEIO
+#define MJ_ERR_IMAGE_SIZE MJ_ERR_IMAGE_SIZE
+#define MJ_ERR_UNSUPPORTED_FILETYPE MJ_ERR_UNSUPPORTED_FILETYPE
+#define MJ_ERR_DEVICE MJ_ERR_DEVICE
+
 /* sampling description of a decoded JPEG (reference: :71-84) */
 typedef struct {
     int h_samp_factor;

@@ -188,7 +188,10 @@ int mjx_compose_batch_device(mjx_ctx *ctx, const mjx_image_desc_t *items_dev, in
                              int block_x, int block_y);
 /* n images in host memory.  Page-locked planes (mjx_host_alloc / cudaHostRegister): one launch working directly on
  * host memory (zero-copy, see mjx_ctx_set_zero_copy); pageable planes: the region under the dropon is staged H2D,
- * blended and staged back through a 3-stream pipeline.  Returns when the host planes hold the result. */
+ * blended and staged back through a 3-stream pipeline.  Returns when the host planes hold the result.
+ * Unlike mjx_compose_batch_device -- which skips, per image, the dropon blocks that fall outside that image's planes -- this
+ * call wants the dropon's whole region inside every plane and returns MJX_ERR_ARG otherwise (the staged path moves the region
+ * as one rectangle); mjx_geometry() crops a dropon to the image, so callers that place dropons with it never see the error. */
 int mjx_compose_batch_host(mjx_ctx *ctx, const mjx_host_image_t *items, int n, const mjx_dropon *d,
                            int block_x, int block_y);
 /* one image given as libjpeg row pointers: rows[c][l] -> block (block_y*v_c + l, block_x*h_c) of component c,
