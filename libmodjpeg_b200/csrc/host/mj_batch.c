@@ -46,7 +46,9 @@ typedef struct {
     size_t          image_bytes, plane_off[MJX_MAX_COMPONENTS];
     int             stride[MJX_MAX_COMPONENTS], hreal[MJX_MAX_COMPONENTS], wreal[MJX_MAX_COMPONENTS];
     const unsigned int *seg_size; /* per slot: bytes of the segment in the slot's slab region, 0xFFFFFFFF: not coded */
+    size_t          seg_cap;      /* bytes per segment in the device slab */
     char           *written;      /* per window image: the output file exists already */
+    int            *group_buf;    /* storage of `group` */
 } batch_t;
 
 static int take(batch_t *b, int limit) {
@@ -220,9 +222,12 @@ static void dev_release(mjx_ctx *ctx, devbufs_t *v) {
 /* One group (images of one geometry) entirely on the device: whole planes up, K2 in HBM, K4 codes the scans, only the
  * entropy-coded segments come back; the workers put libjpeg's markers in front of them.  Images the device cannot code
  * (a coefficient outside the baseline tables, a segment beyond the slab) get their planes back and are left to libjpeg.
- * Returns MJ_OK when the group was handled (per-image results in status / written), another code when nothing was done and
- * the ordinary path should take the group. */
-static int group_on_device(batch_t *b, mjx_ctx *ctx, devbufs_t *v, mjx_dropon *cd, int nthreads, pthread_t *th, unsigned int *seg_size) {
+ * Two halves, so that the device works on one window while the pool decodes the next:
+ *   group_enqueue   planes -> page-locked slab (pool), then H2D, K2, K4 and the read of the segment sizes are QUEUED on the
+ *                   ctx stream; returns without waiting.  MJ_OK: queued; another code: nothing was queued and the ordinary
+ *                   path should take the group.
+ *   group_finish    waits for the stream, fetches the segments, writes the files (pool), hands uncoded images back. */
+static int group_enqueue(batch_t *b, mjx_ctx *ctx, devbufs_t *v, mjx_dropon *cd, int nthreads, pthread_t *th) {
     mj_jpeg_t *ref = &b->jp[b->group[0] - b->w0];
     mjx_scan_t scan;
     {
@@ -245,9 +250,11 @@ static int group_on_device(batch_t *b, mjx_ctx *ctx, devbufs_t *v, mjx_dropon *c
     size_t cap = (b->image_bytes / 4 + 255) & ~(size_t)255;
     if(cap < 65536) cap = 65536;
     if(cap > b->image_bytes) cap = b->image_bytes;
+    b->seg_cap = cap;
     const size_t ng = (size_t)b->ngroup;
     void        *slab = NULL;
-    int          rv = mjx_ctx_pinned_scratch(ctx, b->image_bytes * ng + sizeof(mjx_image_desc_t) * ng, &slab);
+    /* slab: the images' regions, then the descriptors, then the segment sizes the device reports */
+    int rv = mjx_ctx_pinned_scratch(ctx, b->image_bytes * ng + sizeof(mjx_image_desc_t) * ng + 4 * ng + 256, &slab);
     if(rv == MJX_OK) rv = dev_grow(ctx, &v->planes, &v->planes_bytes, b->image_bytes * ng);
     if(rv == MJX_OK) rv = dev_grow(ctx, &v->segs, &v->segs_bytes, cap * ng);
     if(rv == MJX_OK) rv = dev_grow(ctx, &v->sizes, &v->sizes_bytes, 4 * ng);
@@ -257,6 +264,7 @@ static int group_on_device(batch_t *b, mjx_ctx *ctx, devbufs_t *v, mjx_dropon *c
     run_phase(b, 5, nthreads, th); /* whole planes -> page-locked slab */
 
     mjx_image_desc_t *descs = (mjx_image_desc_t *)(b->slab + b->image_bytes * ng);
+    b->seg_size = (unsigned int *)((char *)descs + sizeof(mjx_image_desc_t) * ng);
     memset(descs, 0, sizeof(mjx_image_desc_t) * ng);
     for(int s = 0; s < b->ngroup; s++) {
         mj_jpeg_t *m = &b->jp[b->group[s] - b->w0];
@@ -274,35 +282,44 @@ static int group_on_device(batch_t *b, mjx_ctx *ctx, devbufs_t *v, mjx_dropon *c
     for(int s = 0; s < b->ngroup; s++)
         if(b->status[b->group[s]] != MJ_OK) return MJ_ERR_NULL_DATA; /* (the caller marks the group) */
 
-    const double tk = now_s();
     rv = mjx_copy_h2d(ctx, v->planes, b->slab, b->image_bytes * ng);
     if(rv == MJX_OK) rv = mjx_copy_h2d(ctx, v->descs, descs, sizeof(mjx_image_desc_t) * ng);
     if(rv == MJX_OK) rv = mjx_compose_batch_device(ctx, (const mjx_image_desc_t *)v->descs, b->ngroup, cd, b->g.block_x, b->g.block_y);
     if(rv == MJX_OK) rv = mjx_huffman_encode_batch_device(ctx, (const mjx_image_desc_t *)v->descs, b->ngroup, &scan, v->segs, cap, (uint32_t *)v->sizes);
-    if(rv == MJX_OK) rv = mjx_copy_d2h(ctx, seg_size, v->sizes, 4 * ng);
-    if(rv == MJX_OK) rv = mjx_ctx_sync(ctx);
-    /* the segments, each at the start of its image's slab region (the planes there have been uploaded); an image that was not
-     * coded gets its composed planes back instead */
-    for(int s = 0; rv == MJX_OK && s < b->ngroup; s++) {
-        if(seg_size[s] != 0xFFFFFFFFu) rv = mjx_copy_d2h(ctx, b->slab + (size_t)s * b->image_bytes, (char *)v->segs + (size_t)s * cap, seg_size[s]);
-        else rv = mjx_copy_d2h(ctx, b->slab + (size_t)s * b->image_bytes, (char *)v->planes + (size_t)s * b->image_bytes, b->image_bytes);
-    }
-    if(rv == MJX_OK) rv = mjx_ctx_sync(ctx);
-    b->phase_s[0] += now_s() - tk;
+    if(rv == MJX_OK) rv = mjx_copy_d2h(ctx, (void *)b->seg_size, v->sizes, 4 * ng);
     if(rv != MJX_OK) {
+        mjx_ctx_sync(ctx);
         fprintf(stderr, "libmodjpeg (B200): device batch failed: %s\n", mjx_ctx_last_error(ctx));
         return mjp_map_error(rv);
     }
-    b->seg_size = seg_size;
+    return MJ_OK;
+}
+
+static void group_finish(batch_t *b, mjx_ctx *ctx, devbufs_t *v, int nthreads, pthread_t *th) {
+    const double tw = now_s();
+    int          rv = mjx_ctx_sync(ctx);
+    /* the segments, each at the start of its image's slab region (the planes there have been uploaded); an image that was not
+     * coded gets its composed planes back instead */
+    for(int s = 0; rv == MJX_OK && s < b->ngroup; s++) {
+        if(b->seg_size[s] != 0xFFFFFFFFu) rv = mjx_copy_d2h(ctx, b->slab + (size_t)s * b->image_bytes, (char *)v->segs + (size_t)s * b->seg_cap, b->seg_size[s]);
+        else rv = mjx_copy_d2h(ctx, b->slab + (size_t)s * b->image_bytes, (char *)v->planes + (size_t)s * b->image_bytes, b->image_bytes);
+    }
+    if(rv == MJX_OK) rv = mjx_ctx_sync(ctx);
+    b->phase_s[0] += now_s() - tw; /* what the host WAITED for the device (copies + K2 + K4 beyond what the next window's decode hid) */
+    if(rv != MJX_OK) {
+        fprintf(stderr, "libmodjpeg (B200): device batch failed: %s\n", mjx_ctx_last_error(ctx));
+        for(int s = 0; s < b->ngroup; s++)
+            if(b->status[b->group[s]] == MJ_OK) b->status[b->group[s]] = mjp_map_error(rv);
+        return;
+    }
     run_phase(b, 6, nthreads, th); /* files */
     for(int s = 0; s < b->ngroup; s++) { /* not coded on the device: composed planes back into libjpeg's arrays, phase 4 encodes */
         const int i = b->group[s];
-        if(seg_size[s] == 0xFFFFFFFFu && b->status[i] == MJ_OK) {
+        if(b->seg_size[s] == 0xFFFFFFFFu && b->status[i] == MJ_OK) {
             const int r2 = stage_planes(b, s, &b->jp[i - b->w0], 0);
             if(r2 != MJ_OK) b->status[i] = r2;
         }
     }
-    return MJ_OK;
 }
 
 /* the pipeline on the calling thread's device */
@@ -315,134 +332,174 @@ static int batch_on_device(int n, const mj_blob_t *in, mj_blob_t *out, int *stat
     int window = 4 * nthreads;
     if(window > 256) window = 256;
     if(window > n) window = n;
-    batch_t b;
-    memset(&b, 0, sizeof(b));
-    b.n = n, b.in = in, b.out = out, b.status = status, b.write_options = write_options;
-    pthread_mutex_init(&b.lock, NULL);
-    b.jp = (mj_jpeg_t *)calloc((size_t)window, sizeof(mj_jpeg_t));
-    int       *group = (int *)malloc(sizeof(int) * (size_t)window);
+    /* two window states: while the device works on one window (queued by group_enqueue), the pool decodes the next */
+    batch_t B[2];
+    memset(B, 0, sizeof(B));
+    int result = MJ_OK;
+    for(int k = 0; k < 2; k++) {
+        batch_t *b = &B[k];
+        b->n = n, b->in = in, b->out = out, b->status = status, b->write_options = write_options;
+        pthread_mutex_init(&b->lock, NULL);
+        b->jp = (mj_jpeg_t *)calloc((size_t)window, sizeof(mj_jpeg_t));
+        b->group_buf = (int *)malloc(sizeof(int) * (size_t)window);
+        b->written = (char *)calloc((size_t)window, 1);
+        if(b->jp == NULL || b->group_buf == NULL || b->written == NULL) result = MJ_ERR_MEMORY;
+    }
     char      *done = (char *)malloc((size_t)window);
-    /* a plain baseline file wanted (and MJX_GPU_HUFFMAN not 0): planes, blend and entropy coding of a group stay on the device */
-    const int     on_device = compose && write_options == 0 && mjp_gpu_huffman_mode() != 0;
-    unsigned int *seg_size = (unsigned int *)malloc(sizeof(unsigned int) * (size_t)window);
-    devbufs_t     dv;
-    memset(&dv, 0, sizeof(dv));
-    b.written = (char *)calloc((size_t)window, 1);
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
     mjx_host_image_t *items = (mjx_host_image_t *)malloc(sizeof(mjx_host_image_t) * (size_t)window);
-    int            result = MJ_OK;
+    /* a plain baseline file wanted (and MJX_GPU_HUFFMAN not 0): planes, blend and entropy coding of a group stay on the device */
+    const int      on_device = compose && write_options == 0 && mjp_gpu_huffman_mode() != 0;
+    devbufs_t      dv;
     mjx_dropon    *cd = NULL;
     mjx_layout_t   cd_layout;
     mjx_geometry_t cd_g;
+    batch_t       *pending = NULL; /* the window whose device work is queued and whose files are still to be written */
+    int            cur = 0;
+    memset(&dv, 0, sizeof(dv));
     memset(&cd_layout, 0, sizeof(cd_layout));
     memset(&cd_g, 0, sizeof(cd_g));
-    if(b.jp == NULL || group == NULL || done == NULL || th == NULL || items == NULL || seg_size == NULL || b.written == NULL) {
+    if(result != MJ_OK || done == NULL || th == NULL || items == NULL) {
         result = MJ_ERR_MEMORY;
         goto out;
     }
 
-    for(b.w0 = 0; b.w0 < n; b.w0 = b.w1) {
-        b.w1 = b.w0 + window < n ? b.w0 + window : n;
-        run_phase(&b, 1, nthreads, th); /* entropy decode */
+    for(int w0 = 0; w0 < n;) {
+        batch_t *bp = &B[cur];
+        bp->w0 = w0;
+        bp->w1 = w0 + window < n ? w0 + window : n;
+        w0 = bp->w1;
+        run_phase(bp, 1, nthreads, th); /* entropy decode -- the device works on the pending window meanwhile */
+        if(pending != NULL) {
+            group_finish(pending, ctx, &dv, nthreads, th);
+            run_phase(pending, 4, nthreads, th); /* free; host encode of what the device handed back */
+            pending = NULL;
+        }
 
         /* compose the window group by group (images sharing one geometry share one compiled dropon and one launch) */
         memset(done, 0, (size_t)window);
-        memset(b.written, 0, (size_t)window);
-        for(int k0 = 0; compose && k0 < b.w1 - b.w0; k0++) {
-            if(done[k0] || status[b.w0 + k0] != MJ_OK) continue;
-            mj_jpeg_t *ref = &b.jp[k0];
-            b.ngroup = 0;
-            for(int k = k0; k < b.w1 - b.w0; k++)
-                if(!done[k] && status[b.w0 + k] == MJ_OK && same_geometry(ref, &b.jp[k])) {
-                    group[b.ngroup++] = b.w0 + k;
+        memset(bp->written, 0, (size_t)window);
+        int deferred = 0;
+        for(int k0 = 0; compose && k0 < bp->w1 - bp->w0; k0++) {
+            if(done[k0] || status[bp->w0 + k0] != MJ_OK) continue;
+            mj_jpeg_t *ref = &bp->jp[k0];
+            int       *group = bp->group_buf;
+            bp->ngroup = 0;
+            for(int k = k0; k < bp->w1 - bp->w0; k++)
+                if(!done[k] && status[bp->w0 + k] == MJ_OK && same_geometry(ref, &bp->jp[k])) {
+                    group[bp->ngroup++] = bp->w0 + k;
                     done[k] = 1;
                 }
             mjx_geometry(ref->width, ref->height, ref->sampling.h_factor, ref->sampling.v_factor, d->width, d->height, align, offset_x,
-                         offset_y, &b.g);
-            if(!b.g.visible) continue; /* dropon entirely off these images (reference: src/compose.c:136) */
+                         offset_y, &bp->g);
+            if(!bp->g.visible) continue; /* dropon entirely off these images (reference: src/compose.c:136) */
             mjx_layout_t layout;
             int          rv = mjx_jpeg_layout(ref, &layout);
             /* one compiled dropon is kept across groups and windows while layout and placement repeat */
-            if(rv == MJ_OK && cd != NULL && (memcmp(&layout, &cd_layout, sizeof(layout)) != 0 || memcmp(&b.g, &cd_g, sizeof(b.g)) != 0)) {
+            if(rv == MJ_OK && cd != NULL && (memcmp(&layout, &cd_layout, sizeof(layout)) != 0 || memcmp(&bp->g, &cd_g, sizeof(bp->g)) != 0)) {
                 mjx_dropon_free(cd);
                 cd = NULL;
             }
             if(rv == MJ_OK && cd == NULL) {
                 cd_layout = layout;
-                cd_g = b.g;
-                rv = mjx_dropon_compile(ctx, &cd, d->image, d->alpha, d->width, d->height, d->colorspace, &layout, b.g.blockoffset_x,
-                                        b.g.blockoffset_y, b.g.crop_x, b.g.crop_y, b.g.crop_w, b.g.crop_h, 0);
+                cd_g = bp->g;
+                rv = mjx_dropon_compile(ctx, &cd, d->image, d->alpha, d->width, d->height, d->colorspace, &layout, bp->g.blockoffset_x,
+                                        bp->g.blockoffset_y, bp->g.crop_x, bp->g.crop_y, bp->g.crop_w, bp->g.crop_h, 0);
                 if(rv == MJX_ERR_UNSUPPORTED) fprintf(stderr, "Unsupported color conversion request\n");
                 rv = mjp_map_error(rv);
             }
             if(rv == MJ_OK && on_device) {
-                b.ncomp = layout.ncomp;
-                b.group = group;
-                if(group_on_device(&b, ctx, &dv, cd, nthreads, th, seg_size) == MJ_OK) continue;
+                bp->ncomp = layout.ncomp;
+                bp->group = group;
+                if(group_enqueue(bp, ctx, &dv, cd, nthreads, th) == MJ_OK) {
+                    /* the last group of the window is left running while the next window is decoded; a group with others
+                     * behind it in this window is finished at once (its slab and device buffers are needed again) */
+                    int more = 0;
+                    for(int k = k0 + 1; k < bp->w1 - bp->w0; k++) more |= !done[k] && status[bp->w0 + k] == MJ_OK;
+                    if(more) group_finish(bp, ctx, &dv, nthreads, th);
+                    else deferred = 1;
+                    continue;
+                }
                 /* (not a file the device codes, or no memory for it: the ordinary path below) */
                 int bad = 0;
-                for(int s = 0; s < b.ngroup; s++) bad |= status[group[s]] != MJ_OK;
+                for(int s = 0; s < bp->ngroup; s++) bad |= status[group[s]] != MJ_OK;
                 if(bad) rv = MJ_ERR_NULL_DATA;
             }
             if(rv == MJ_OK) {
-                b.ncomp = layout.ncomp;
-                b.region_bytes = 0;
-                for(int c = 0; c < b.ncomp; c++) {
-                    mjx_dropon_dims(cd, c, &b.wb[c], &b.hb[c]);
-                    b.comp_off[c] = b.region_bytes;
-                    b.region_bytes += ((size_t)b.wb[c] * (size_t)b.hb[c] * 128 + 255) & ~(size_t)255;
+                bp->ncomp = layout.ncomp;
+                bp->region_bytes = 0;
+                for(int c = 0; c < bp->ncomp; c++) {
+                    mjx_dropon_dims(cd, c, &bp->wb[c], &bp->hb[c]);
+                    bp->comp_off[c] = bp->region_bytes;
+                    bp->region_bytes += ((size_t)bp->wb[c] * (size_t)bp->hb[c] * 128 + 255) & ~(size_t)255;
                 }
                 void *slab = NULL;
-                rv = mjp_map_error(mjx_ctx_pinned_scratch(ctx, b.region_bytes * (size_t)b.ngroup, &slab));
-                b.slab = (char *)slab;
+                rv = mjp_map_error(mjx_ctx_pinned_scratch(ctx, bp->region_bytes * (size_t)bp->ngroup, &slab));
+                bp->slab = (char *)slab;
             }
             if(rv == MJ_OK) {
-                b.group = group;
-                run_phase(&b, 2, nthreads, th); /* rows under the dropon -> page-locked slab */
-                for(int s = 0; s < b.ngroup; s++) {
-                    mj_jpeg_t *m = &b.jp[group[s] - b.w0];
+                bp->group = group;
+                run_phase(bp, 2, nthreads, th); /* rows under the dropon -> page-locked slab */
+                for(int s = 0; s < bp->ngroup; s++) {
+                    mj_jpeg_t *m = &bp->jp[group[s] - bp->w0];
                     memset(&items[s], 0, sizeof(items[s]));
-                    for(int c = 0; c < b.ncomp; c++) {
-                        items[s].plane[c] = (int16_t *)(b.slab + (size_t)s * b.region_bytes + b.comp_off[c]);
-                        items[s].stride_blocks[c] = items[s].wreal[c] = b.wb[c];
-                        items[s].rows[c] = items[s].hreal[c] = b.hb[c];
+                    for(int c = 0; c < bp->ncomp; c++) {
+                        items[s].plane[c] = (int16_t *)(bp->slab + (size_t)s * bp->region_bytes + bp->comp_off[c]);
+                        items[s].stride_blocks[c] = items[s].wreal[c] = bp->wb[c];
+                        items[s].rows[c] = items[s].hreal[c] = bp->hb[c];
                         items[s].q[c] = m->cinfo.comp_info[c].quant_table ? m->cinfo.comp_info[c].quant_table->quantval : NULL;
                         if(items[s].q[c] == NULL) status[group[s]] = MJ_ERR_NULL_DATA;
                     }
                 }
                 int ok = 1;
-                for(int s = 0; s < b.ngroup; s++) ok &= status[group[s]] == MJ_OK;
+                for(int s = 0; s < bp->ngroup; s++) ok &= status[group[s]] == MJ_OK;
                 if(ok) {
                     const double tk = now_s();
-                    rv = mjx_compose_batch_host(ctx, items, b.ngroup, cd, 0, 0); /* K2: one launch for the group */
-                    b.phase_s[0] += now_s() - tk;
+                    rv = mjx_compose_batch_host(ctx, items, bp->ngroup, cd, 0, 0); /* K2: one launch for the group */
+                    bp->phase_s[0] += now_s() - tk;
                     if(rv != MJX_OK) fprintf(stderr, "libmodjpeg (B200): batch compose failed: %s\n", mjx_ctx_last_error(ctx));
                     rv = mjp_map_error(rv);
                 }
                 else rv = MJ_ERR_NULL_DATA;
-                if(rv == MJ_OK) run_phase(&b, 3, nthreads, th); /* slab -> libjpeg's arrays */
+                if(rv == MJ_OK) run_phase(bp, 3, nthreads, th); /* slab -> libjpeg's arrays */
             }
             if(rv != MJ_OK)
-                for(int s = 0; s < b.ngroup; s++)
+                for(int s = 0; s < bp->ngroup; s++)
                     if(status[group[s]] == MJ_OK) status[group[s]] = rv;
         }
-        run_phase(&b, 4, nthreads, th); /* entropy encode + free */
+        if(deferred) {
+            pending = bp; /* its files are written after the next window's decode */
+            cur ^= 1;
+        }
+        else run_phase(bp, 4, nthreads, th); /* entropy encode + free */
     }
-    if(getenv("MJ_BATCH_TRACE") != NULL)
-        fprintf(stderr, "mj_compose_batch: %d images, %d threads: decode %.3f s, stage-in %.3f s, K2%s %.3f s, stage-out %.3f s, %s %.3f s\n", n,
-                nthreads, b.phase_s[1], b.phase_s[2] + b.phase_s[5], on_device ? " + copies + K4" : "", b.phase_s[0], b.phase_s[3],
-                on_device ? "files (markers + segment) + host encode" : "encode", b.phase_s[4] + b.phase_s[6]);
+    if(pending != NULL) {
+        group_finish(pending, ctx, &dv, nthreads, th);
+        run_phase(pending, 4, nthreads, th);
+        pending = NULL;
+    }
+    if(getenv("MJ_BATCH_TRACE") != NULL) {
+        double ps[7];
+        for(int k = 0; k < 7; k++) ps[k] = B[0].phase_s[k] + B[1].phase_s[k];
+        fprintf(stderr, "mj_compose_batch: %d images, %d threads: decode %.3f s, stage-in %.3f s, %s %.3f s, stage-out %.3f s, %s %.3f s\n", n,
+                nthreads, ps[1], ps[2] + ps[5], on_device ? "waited for the device (copies + K2 + K4 not hidden by the next decode)" : "K2", ps[0], ps[3],
+                on_device ? "files (markers + segment) + host encode" : "encode", ps[4] + ps[6]);
+    }
 out:
-    if(ctx != NULL) dev_release(ctx, &dv);
-    free(seg_size);
-    free(b.written);
+    if(ctx != NULL) {
+        mjx_ctx_sync(ctx);
+        dev_release(ctx, &dv);
+    }
     if(cd != NULL) mjx_dropon_free(cd);
-    free(b.jp);
-    free(group);
+    for(int k = 0; k < 2; k++) {
+        free(B[k].jp);
+        free(B[k].group_buf);
+        free(B[k].written);
+        pthread_mutex_destroy(&B[k].lock);
+    }
     free(done);
     free(th);
     free(items);
-    pthread_mutex_destroy(&b.lock);
     return result;
 }
 
