@@ -820,6 +820,16 @@ int mjx_compose_batch_host(mjx_ctx *ctx, const mjx_host_image_t *items, int n, c
     for(int s = 0; s < P; s++) MJX_CUDA(ctx, cudaStreamWaitEvent(ctx->pipe[s], start, 0));
     cudaEventDestroy(start);
 
+    // an error in the middle of the pipeline: copies into the caller's planes are in flight on the other streams -- they must
+    // not outlive the call
+#define PIPE_CUDA(call)                                                        \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if(e__ != cudaSuccess) {                                               \
+            for(int k__ = 0; k__ < P; k__++) cudaStreamSynchronize(ctx->pipe[k__]); \
+            return mjx::fail(ctx, e__, #call);                                 \
+        }                                                                      \
+    } while(0)
     for(int i = 0; i < n; i++) {
         const int         s = i % P;
         cudaStream_t      st = ctx->pipe[s];
@@ -835,24 +845,28 @@ int mjx_compose_batch_host(mjx_ctx *ctx, const mjx_host_image_t *items, int n, c
             desc->hreal[c] = dc.hb;
             memcpy(desc->q[c], items[i].q[c], 128);
         }
-        MJX_CUDA(ctx, cudaMemcpyAsync(ddev + desc_sz * s, desc, sizeof(*desc), cudaMemcpyHostToDevice, st));
+        PIPE_CUDA(cudaMemcpyAsync(ddev + desc_sz * s, desc, sizeof(*desc), cudaMemcpyHostToDevice, st));
         for(int c = 0; c < ncomp; c++) {
             const DropComp &dc = d->view.comp[c];
             const size_t    sp = (size_t)items[i].stride_blocks[c] * 128, wbytes = (size_t)dc.wb * 128;
             const char     *src = (const char *)items[i].plane[c] + ((size_t)block_y * dc.vs * items[i].stride_blocks[c] + (size_t)block_x * dc.hs) * 128;
-            if(sp == wbytes) MJX_CUDA(ctx, cudaMemcpyAsync(base + off[c], src, wbytes * dc.hb, cudaMemcpyHostToDevice, st));
-            else MJX_CUDA(ctx, cudaMemcpy2DAsync(base + off[c], wbytes, src, sp, wbytes, dc.hb, cudaMemcpyHostToDevice, st));
+            if(sp == wbytes) PIPE_CUDA(cudaMemcpyAsync(base + off[c], src, wbytes * dc.hb, cudaMemcpyHostToDevice, st));
+            else PIPE_CUDA(cudaMemcpy2DAsync(base + off[c], wbytes, src, sp, wbytes, dc.hb, cudaMemcpyHostToDevice, st));
         }
         const cudaError_t e = run_k2(ctx, st, (char *)ctx->scratch + scr_sz * s, (const mjx_image_desc_t *)(ddev + desc_sz * s), 1, d, 0, 0, false);
-        if(e != cudaSuccess) return fail(ctx, e, "k2_compose_kernel");
+        if(e != cudaSuccess) {
+            for(int k = 0; k < P; k++) cudaStreamSynchronize(ctx->pipe[k]); // copies into caller memory must not outlive the call
+            return fail(ctx, e, "k2_compose_kernel");
+        }
         for(int c = 0; c < ncomp; c++) {
             const DropComp &dc = d->view.comp[c];
             const size_t    sp = (size_t)items[i].stride_blocks[c] * 128, wbytes = (size_t)dc.wb * 128;
             char           *dst = (char *)items[i].plane[c] + ((size_t)block_y * dc.vs * items[i].stride_blocks[c] + (size_t)block_x * dc.hs) * 128;
-            if(sp == wbytes) MJX_CUDA(ctx, cudaMemcpyAsync(dst, base + off[c], wbytes * dc.hb, cudaMemcpyDeviceToHost, st));
-            else MJX_CUDA(ctx, cudaMemcpy2DAsync(dst, sp, base + off[c], wbytes, wbytes, dc.hb, cudaMemcpyDeviceToHost, st));
+            if(sp == wbytes) PIPE_CUDA(cudaMemcpyAsync(dst, base + off[c], wbytes * dc.hb, cudaMemcpyDeviceToHost, st));
+            else PIPE_CUDA(cudaMemcpy2DAsync(dst, sp, base + off[c], wbytes, wbytes, dc.hb, cudaMemcpyDeviceToHost, st));
         }
     }
+#undef PIPE_CUDA
     for(int s = 0; s < P; s++) MJX_CUDA(ctx, cudaStreamSynchronize(ctx->pipe[s]));
     return MJX_OK;
 }

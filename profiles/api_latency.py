@@ -51,6 +51,10 @@ def case(name, data, raw, align, reps):
                         ("tint", lambda: j.effect_tint(2, -2), lambda: jr.tint(2, -2)),
                         ("pixelate", lambda: j.effect_pixelate(), lambda: jr.pixelate())]:
         out[f"mj_effect_{eff}_ms"] = {"b200": med(fo, reps), "reference_1_thread": med(fr, max(3, reps // 4))}
+    # the writer: libjpeg's entropy encoder on the host (what mj_write_jpeg_to_memory and the reference do) against K4 behind
+    # the same markers (mjx_write_jpeg_to_memory_device: planes staged to the device, six launches, the segment back)
+    j.write_jpeg_to_memory_device(0)
+    out["mj_write_jpeg_to_memory_ms"] = {"host_libjpeg": med(lambda: j.write_jpeg_to_memory(0), reps), "device_k4": med(lambda: j.write_jpeg_to_memory_device(0), reps)}
     return out
 
 
