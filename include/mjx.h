@@ -228,6 +228,17 @@ int mjx_huffman_encode_rows_host(mjx_ctx *ctx, int ncomp, const int16_t *const *
                                  const int *vrows, const int *wreal, const int *hreal, const mjx_scan_t *scan,
                                  unsigned char **out, size_t *len);
 
+/* ---- K5: Huffman decoding of a baseline scan on the device (second half) ----------------------------
+ *      replaces, for mj_read_jpeg_from_memory (reference: src/image.c:33-118), the entropy decoder jpeg_read_coefficients
+ *      runs on the host (libjpeg jdhuff.c decode_mcu): 8-bit sequential DCT, ONE scan with every component, no restart
+ *      markers.  data_dev + offsets[i] .. + lengths[i]: image i's entropy-coded segment as it stands in the file (byte
+ *      stuffing included, from behind the SOS header; bytes behind the last MCU are ignored).  offsets / lengths are HOST
+ *      arrays.  The planes the descriptors name are overwritten (padding blocks included, like libjpeg's arrays); wreal /
+ *      hreal / q of the descriptors are not looked at.  status_dev[i] != 0: not decoded (a bit pattern that is no code, a run
+ *      past coefficient 63, a stream with fewer blocks than the frame) -- let libjpeg read that image.  Asynchronous. */
+int mjx_huffman_decode_batch_device(mjx_ctx *ctx, const void *data_dev, const uint64_t *offsets, const uint32_t *lengths, int n,
+                                    const mjx_scan_t *scan, const mjx_image_desc_t *items_dev, uint32_t *status_dev);
+
 /* ---- K3: coefficient effects (replaces src/effect.c:28-222) --------------------------- */
 int mjx_effects_batch_device(mjx_ctx *ctx, const mjx_image_desc_t *items_dev, int n, int ncomp,
                              const mjx_effect_op_t *ops, int nops);

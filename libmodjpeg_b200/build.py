@@ -26,7 +26,7 @@ INCLUDE = os.path.join(ROOT, "include")
 JPEG_INC = os.path.join(ROOT, "third_party", "jpeg62")
 PNG_INC = os.path.join(ROOT, "third_party", "png16")
 
-CUDA_SOURCES = ["mjx_api.cu", "k1_dropon.cu", "k1_lists.cu", "k2_compose.cu", "k2_generic_op.cu", "k3_effects.cu", "k4_huffman.cu"]
+CUDA_SOURCES = ["mjx_api.cu", "k1_dropon.cu", "k1_lists.cu", "k2_compose.cu", "k2_generic_op.cu", "k3_effects.cu", "k4_huffman.cu", "k5_huffman_decode.cu"]
 HOST_SOURCES = ["mj_jpegio.c", "mj_image.c", "mj_dropon.c", "mj_compose.c", "mj_effect.c", "mj_device.c", "mj_batch.c", "mj_coalesce.c"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -137,6 +137,7 @@ def load_mjx() -> C.CDLL:
     L.mjx_compose_batch_device.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int]
     L.mjx_compose_batch_host.argtypes = [vp, C.POINTER(HostImage), C.c_int, vp, C.c_int, C.c_int]
     L.mjx_compose_rows_host.argtypes = [vp, C.c_int, vp, vp, vp]
+    L.mjx_huffman_decode_batch_device.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp]
     L.mjx_huffman_encode_batch_device.argtypes = [vp, vp, C.c_int, vp, vp, C.c_size_t, vp]
     L.mjx_effects_batch_device.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(EffectOp), C.c_int]
     L.mjx_effects_rows_host.argtypes = [vp, C.c_int, vp, ip, ip, vp, C.POINTER(EffectOp), C.c_int]
@@ -385,6 +386,17 @@ class Engine:
         self._check(self.lib.mjx_huffman_encode_batch_device(self.ctx, C.c_void_p(items_dev), n, C.byref(scan), C.c_void_p(out_dev),
                                                              C.c_size_t(out_stride), C.c_void_p(sizes_dev)), "mjx_huffman_encode_batch_device")
 
+    # ---- K5 -----------------------------------------------------------------------------
+    def huffman_decode_batch_device(self, data_dev: int, offsets: np.ndarray, lengths: np.ndarray, n: int, scan: "Scan", items_dev: int,
+                                    status_dev: int) -> None:
+        """entropy-coded segments (device memory, offsets / lengths on the host) -> coefficient planes of n device-resident
+        images (asynchronous on the ctx stream)"""
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        lengths = np.ascontiguousarray(lengths, np.uint32)
+        assert offsets.size >= n and lengths.size >= n
+        self._check(self.lib.mjx_huffman_decode_batch_device(self.ctx, C.c_void_p(data_dev), C.c_void_p(offsets.ctypes.data), C.c_void_p(lengths.ctypes.data), n,
+                                                             C.byref(scan), C.c_void_p(items_dev), C.c_void_p(status_dev)), "mjx_huffman_decode_batch_device")
+
 
 class HuffTable(C.Structure):
     _fields_ = [("bits", C.c_uint8 * 17), ("vals", C.c_uint8 * 256)]
@@ -449,6 +461,65 @@ def standard_scan(width: int, height: int, samp: list[tuple[int, int]], chroma_f
     _fill_table(s.dc[1], STD_DC_CHROMA)
     _fill_table(s.ac[1], STD_AC_CHROMA)
     return s
+
+
+def scan_from_jpeg(data: bytes) -> tuple[Scan, int, dict]:
+    """Parse the markers of a baseline JPEG up to its first SOS: returns (the scan as K4 / K5 want it -- the FILE's Huffman
+    tables, sampling factors, table selectors, MCU grid --, offset of the entropy-coded segment, frame info).  Raises
+    ValueError for what the device decoder does not take: not SOF0/SOF1 8-bit, restart intervals, a scan that does not hold
+    every component."""
+    if data[:2] != b"\xff\xd8":
+        raise ValueError("not a JPEG")
+    i, frame, tables, dri = 2, None, {}, 0
+    while True:
+        if data[i] != 0xFF:
+            raise ValueError("marker expected")
+        while data[i + 1] == 0xFF:
+            i += 1
+        m = data[i + 1]
+        n = (data[i + 2] << 8) | data[i + 3]
+        seg = data[i + 4:i + 2 + n]
+        if m in (0xC0, 0xC1):
+            if seg[0] != 8:
+                raise ValueError("not 8-bit")
+            frame = {"height": (seg[1] << 8) | seg[2], "width": (seg[3] << 8) | seg[4],
+                     "comps": [(seg[6 + 3 * k], seg[7 + 3 * k] >> 4, seg[7 + 3 * k] & 15, seg[8 + 3 * k]) for k in range(seg[5])]}
+        elif 0xC2 <= m <= 0xCF and m not in (0xC4, 0xC8, 0xCC):
+            raise ValueError("not a sequential Huffman frame")
+        elif m == 0xC4:
+            k = 0
+            while k < len(seg):
+                tc, th = seg[k] >> 4, seg[k] & 15
+                counts = list(seg[k + 1:k + 17])
+                nv = sum(counts)
+                tables[(tc, th)] = (counts, list(seg[k + 17:k + 17 + nv]))
+                k += 17 + nv
+        elif m == 0xDD:
+            dri = (seg[0] << 8) | seg[1]
+        elif m == 0xDA:
+            if frame is None or dri != 0 or seg[0] != len(frame["comps"]):
+                raise ValueError("restart intervals or a scan without every component")
+            s = Scan()
+            s.ncomp = seg[0]
+            ids = [c[0] for c in frame["comps"]]
+            for k in range(seg[0]):
+                cid, sel = seg[1 + 2 * k], seg[2 + 2 * k]
+                if cid != ids[k]:
+                    raise ValueError("scan components out of frame order")
+                s.h_samp[k], s.v_samp[k] = frame["comps"][k][1], frame["comps"][k][2]
+                s.dc_tbl[k], s.ac_tbl[k] = sel >> 4, sel & 15
+            max_h, max_v = max(c[1] for c in frame["comps"]), max(c[2] for c in frame["comps"])
+            if s.ncomp == 1:
+                h0, v0 = frame["comps"][0][1], frame["comps"][0][2]
+                s.mcus_per_row = -(-(frame["width"] * h0) // (8 * max_h))
+                s.mcu_rows = -(-(frame["height"] * v0) // (8 * max_v))
+            else:
+                s.mcus_per_row, s.mcu_rows = -(-frame["width"] // (8 * max_h)), -(-frame["height"] // (8 * max_v))
+            for (tc, th), spec in tables.items():
+                if th < 4:
+                    _fill_table(s.dc[th] if tc == 0 else s.ac[th], spec)
+            return s, i + 2 + n, frame
+        i += 2 + n
 
 
 def make_host_image(planes: list[np.ndarray], qtables: list[np.ndarray], real_dims=None):
