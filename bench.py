@@ -642,6 +642,39 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
         except Exception as e:  # noqa: BLE001
             other["k4_huffman_encode"] = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
 
+        # K5: Huffman decoding of every image of the batch on the device (the entropy decoder behind mj_read_jpeg_from_memory,
+        # reference src/image.c:94): entropy-coded segments resident in HBM -> coefficient planes in HBM (the batch's own slab:
+        # what is decoded is what was there before the timed steps)
+        try:
+            parsed = [capi.scan_from_jpeg(jb) for jb in jpegs]
+            segs = [jb[off:] for jb, (_, off, _) in zip(jpegs, parsed)]
+            seg_off = np.concatenate([[0], np.cumsum([(len(sg) + 255) // 256 * 256 for sg in segs])]).astype(np.int64)
+            blob = np.zeros(int(seg_off[-1]) + 256, np.uint8)
+            for k, sg in enumerate(segs):
+                blob[int(seg_off[k]):int(seg_off[k]) + len(sg)] = np.frombuffer(sg, np.uint8)
+            blob_dev = torch.from_numpy(blob).to(dev)
+            offs = np.array([seg_off[(lo + i) % N_BASES] for i in range(n)], np.uint64)
+            lens = np.array([len(segs[(lo + i) % N_BASES]) for i in range(n)], np.uint32)
+            st_dev = torch.zeros(n, dtype=torch.int32, device=dev)
+            ms = timed(lambda: engine.huffman_decode_batch_device(blob_dev.data_ptr(), offs, lens, n, parsed[0][0], descs_dev.data_ptr(), st_dev.data_ptr()), 3)
+            ok = int((st_dev.cpu().numpy() == 0).sum())
+            same = bool(torch.equal(slab[0], torch.from_numpy(base_flat[lo % N_BASES]).to(dev)))
+            hj = M.Jpeg()
+            t_h = time.perf_counter()
+            for _ in range(8):
+                assert hj.read_jpeg_from_memory(jpegs[0]) == 0
+            host_ms = 1e3 * (time.perf_counter() - t_h) / 8
+            in_b, out_b = int(lens.astype(np.int64).sum()), n * image_bytes
+            other["k5_huffman_decode"] = {"ms": ms, "images": n, "decoded": ok, "subsequences_per_image": int((lens[0] * 8 + 1023) // 1024), "first_image_equals_libjpeg": same, "images_per_s": n / (ms * 1e-3),
+                                          "bytes_in": in_b, "bytes_out": out_b, "algorithmic_bytes": in_b + out_b,
+                                          "achieved_gbs": (in_b + out_b) / (ms * 1e-3) / 1e9, "host_libjpeg_ms_per_image_1_thread": host_ms,
+                                          "note": "one launch, one CTA per image: planes zeroed, un-stuffing, entry states of the 1024-bit subsequences settled "
+                                                  "in rounds, write pass, DC prefix sums; host figure: mj_read_jpeg_from_memory of one such image on one core "
+                                                  "(libjpeg's jpeg_read_coefficients), the decoder the reference uses"}
+            del blob_dev
+        except Exception as e:  # noqa: BLE001
+            other["k5_huffman_decode"] = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+
     # ---- parity of the timed path against the unmodified reference (rank 0, outside every timed region) ----
     parity = None
     if rank == 0 and not args.no_parity:

@@ -56,7 +56,7 @@ struct DecParams {
     const DecTable         *tables; // [8]: 0..3 DC, 4..7 AC
     uint32_t               *words;  // [n][words_stride] un-stuffed stream
     size_t                  words_stride;
-    uint2                  *entry;  // [n][sub_stride] state at the start of a subsequence: x = bit position, y = block-in-MCU | z << 8 | bad << 16
+    uint2                  *entry;  // [n][sub_stride] state at the start of a subsequence: x = bit position, y = block-in-MCU | z << 8
     uint2                  *exits;  // [n][sub_stride]
     uint32_t               *cnt;    // [n][sub_stride] blocks completed inside the subsequence, then their exclusive prefix sum
     unsigned char          *dirty;  // [n][2][sub_stride] entry state changed: decode again (this round / the next)
@@ -111,10 +111,13 @@ struct DecState {
     int      z; // next coefficient in zigzag order, 0: the DC code comes next
     int      bad;
 };
-__device__ __forceinline__ uint2 pack_state(const DecState &s) { return make_uint2(s.p, (uint32_t)s.b | ((uint32_t)s.z << 8) | ((uint32_t)s.bad << 16)); }
+// (`bad` is NOT part of the state that travels between subsequences: a decoder in a wrong state meets invalid codes all the
+// time, and carrying the flag along would keep it from ever agreeing with the right one.  The write pass, which starts every
+// subsequence in its exact state, raises it afresh.)
+__device__ __forceinline__ uint2 pack_state(const DecState &s) { return make_uint2(s.p, (uint32_t)s.b | ((uint32_t)s.z << 8)); }
 __device__ __forceinline__ DecState unpack_state(uint2 u) {
     DecState s;
-    s.p = u.x, s.b = (int)(u.y & 0xffu), s.z = (int)((u.y >> 8) & 0xffu), s.bad = (int)((u.y >> 16) & 1u);
+    s.p = u.x, s.b = (int)(u.y & 0xffu), s.z = (int)((u.y >> 8) & 0xffu), s.bad = 0;
     return s;
 }
 
