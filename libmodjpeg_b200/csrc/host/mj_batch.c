@@ -41,7 +41,7 @@ typedef struct {
     int             ncomp;
     mjx_geometry_t  g;
     int             write_options;
-    double          phase_s[7]; /* MJ_BATCH_TRACE=1: seconds per phase ([0] = K2) */
+    double          phase_s[9]; /* MJ_BATCH_TRACE=1: seconds per phase ([0] = K2 / waiting for the device) */
     /* phases 5 / 6: whole planes to the device, files from device-coded segments (MJX_GPU_HUFFMAN=1) */
     size_t          image_bytes, plane_off[MJX_MAX_COMPONENTS];
     int             stride[MJX_MAX_COMPONENTS], hreal[MJX_MAX_COMPONENTS], wreal[MJX_MAX_COMPONENTS];
@@ -49,6 +49,15 @@ typedef struct {
     size_t          seg_cap;      /* bytes per segment in the device slab */
     char           *written;      /* per window image: the output file exists already */
     int            *group_buf;    /* storage of `group` */
+    /* phases 7 / 8: the window never leaves the device (K5 decodes it there): header-only reads, entropy-coded segments to the slab */
+    size_t         *ent_off;      /* per window image: where its entropy-coded segment starts in the input */
+    mjx_scan_t     *in_scan;      /* per window image: its scan with the file's tables */
+    char           *eligible;     /* per window image: header read, the device can decode the scan */
+    size_t         *seg_in_off;   /* per slot: offset of the segment in the slab */
+    int             full;         /* this window was queued by window_enqueue_full */
+    int             out_by_offset; /* phase 6: the slot's segment lies at seg_in_off[s], not at s * image_bytes */
+    int             vrows[MJX_MAX_COMPONENTS];
+    uint32_t       *dec_status;   /* per slot: K5's verdict (in the slab, behind seg_size) */
 } batch_t;
 
 static int take(batch_t *b, int limit) {
@@ -131,6 +140,26 @@ static void *worker(void *arg) {
                 if(rv != MJ_OK) b->status[i] = rv;
             }
         }
+        else if(b->phase == 7) { /* markers only: the frame, the tables, where the entropy-coded segment starts */
+            int k = take(b, b->w1 - b->w0);
+            if(k < 0) break;
+            const int i = b->w0 + k;
+            mj_init_jpeg(&b->jp[k]);
+            b->eligible[k] = 0;
+            if(b->in[i].data == NULL) {
+                b->status[i] = MJ_ERR_NULL_DATA;
+                continue;
+            }
+            const int rv = mjp_read_header_only(&b->jp[k], b->in[i].data, b->in[i].len, &b->ent_off[k], &b->in_scan[k]);
+            if(rv == MJ_OK) b->eligible[k] = 1;
+            else if(rv != MJ_ERR_UNSUPPORTED_FILETYPE) b->status[i] = rv; /* (another kind of JPEG: the window takes the ordinary path) */
+        }
+        else if(b->phase == 8) { /* entropy-coded segments -> page-locked slab */
+            int s = take(b, b->ngroup);
+            if(s < 0) break;
+            const int i = b->group[s], k = i - b->w0;
+            memcpy(b->slab + b->seg_in_off[s], b->in[i].data + b->ent_off[k], b->in[i].len - b->ent_off[k]);
+        }
         else if(b->phase == 5) { /* whole planes -> page-locked slab */
             int s = take(b, b->ngroup);
             if(s < 0) break;
@@ -147,7 +176,9 @@ static void *worker(void *arg) {
             size_t         head_len = 0;
             mjx_scan_t     scan;
             int            rv = mjp_scan_headers(&b->jp[i - b->w0], &head, &head_len, &scan);
-            if(rv == MJ_OK) rv = mjp_assemble_file(&b->out[i].data, &b->out[i].len, head, head_len, (const unsigned char *)b->slab + (size_t)s * b->image_bytes, b->seg_size[s]);
+            if(rv == MJ_OK)
+                rv = mjp_assemble_file(&b->out[i].data, &b->out[i].len, head, head_len,
+                                       (const unsigned char *)b->slab + (b->out_by_offset ? b->seg_in_off[s] : (size_t)s * b->image_bytes), b->seg_size[s]);
             free(head);
             if(rv == MJ_OK) b->written[i - b->w0] = 1;
             else b->status[i] = rv;
@@ -197,8 +228,8 @@ static int same_geometry(const mj_jpeg_t *a, const mj_jpeg_t *b) {
 
 /* Device buffers of the device-resident path, kept across groups and windows */
 typedef struct {
-    void  *planes, *segs, *sizes, *descs;
-    size_t planes_bytes, segs_bytes, sizes_bytes, descs_bytes;
+    void  *planes, *segs, *sizes, *descs, *input, *dstatus;
+    size_t planes_bytes, segs_bytes, sizes_bytes, descs_bytes, input_bytes, dstatus_bytes;
 } devbufs_t;
 
 static int dev_grow(mjx_ctx *ctx, void **p, size_t *have, size_t want) {
@@ -216,6 +247,8 @@ static void dev_release(mjx_ctx *ctx, devbufs_t *v) {
     if(v->segs) mjx_device_free(ctx, v->segs);
     if(v->sizes) mjx_device_free(ctx, v->sizes);
     if(v->descs) mjx_device_free(ctx, v->descs);
+    if(v->input) mjx_device_free(ctx, v->input);
+    if(v->dstatus) mjx_device_free(ctx, v->dstatus);
     memset(v, 0, sizeof(*v));
 }
 
@@ -322,14 +355,225 @@ static void group_finish(batch_t *b, mjx_ctx *ctx, devbufs_t *v, int nthreads, p
     }
 }
 
+/* A window that never leaves the device: its images share one geometry and one set of Huffman tables and the device can decode
+ * their scans (K5).  Only JPEG bytes cross PCIe, in both directions:
+ *   window_enqueue_full   entropy-coded segments -> slab (pool) -> HBM, K5 decodes them into the planes, K2 blends, K4 codes
+ *                         the scans; queued on the ctx stream, returns without waiting
+ *   window_finish_full    waits, fetches the output segments, writes the files (pool); an image K5 or K4 handed back goes
+ *                         through the ordinary calls on the host (mj_read_jpeg_from_memory -> mj_compose -> mj_write_jpeg_to_memory)
+ * Returns MJ_OK when queued; another code when the window is not of that kind (nothing was queued, the header-only objects are
+ * freed) and the ordinary path has to read it. */
+static int window_enqueue_full(batch_t *b, mjx_ctx *ctx, devbufs_t *v, mjx_dropon **cd, mjx_layout_t *cd_layout, mjx_geometry_t *cd_g, mj_dropon_t *d,
+                               unsigned int align, int offset_x, int offset_y, int nthreads, pthread_t *th) {
+    const int nw = b->w1 - b->w0;
+    int       rv = MJ_OK, ref_k = -1;
+    b->ngroup = 0;
+    for(int k = 0; k < nw; k++) {
+        if(b->status[b->w0 + k] != MJ_OK) continue; /* undecodable: reported, not part of the group */
+        if(!b->eligible[k]) rv = MJ_ERR_UNSUPPORTED_FILETYPE;
+        else if(ref_k < 0) ref_k = k;
+        else if(!same_geometry(&b->jp[ref_k], &b->jp[k]) || memcmp(&b->in_scan[ref_k], &b->in_scan[k], sizeof(mjx_scan_t)) != 0) rv = MJ_ERR_UNSUPPORTED_FILETYPE;
+        b->group_buf[b->ngroup++] = b->w0 + k;
+    }
+    mj_jpeg_t *ref = ref_k >= 0 ? &b->jp[ref_k] : NULL;
+    mjx_scan_t out_scan;
+    if(rv == MJ_OK && ref == NULL) rv = MJ_ERR_UNSUPPORTED_FILETYPE;
+    if(rv == MJ_OK) {
+        mjx_geometry(ref->width, ref->height, ref->sampling.h_factor, ref->sampling.v_factor, d->width, d->height, align, offset_x, offset_y, &b->g);
+        if(!b->g.visible) rv = MJ_ERR_UNSUPPORTED_FILETYPE; /* nothing to blend: the ordinary path transcodes */
+    }
+    if(rv == MJ_OK) {
+        unsigned char *head = NULL;
+        size_t         head_len = 0;
+        rv = mjp_scan_headers(ref, &head, &head_len, &out_scan);
+        free(head);
+    }
+    mjx_layout_t layout;
+    if(rv == MJ_OK) rv = mjp_layout_of(ref, &layout);
+    if(rv == MJ_OK && layout.ncomp > MJX_MAX_COMPONENTS) rv = MJ_ERR_UNSUPPORTED_FILETYPE;
+    if(rv == MJ_OK && *cd != NULL && (memcmp(&layout, cd_layout, sizeof(layout)) != 0 || memcmp(&b->g, cd_g, sizeof(b->g)) != 0)) {
+        mjx_dropon_free(*cd);
+        *cd = NULL;
+    }
+    if(rv == MJ_OK && *cd == NULL) {
+        *cd_layout = layout;
+        *cd_g = b->g;
+        const int crv = mjx_dropon_compile(ctx, cd, d->image, d->alpha, d->width, d->height, d->colorspace, &layout, b->g.blockoffset_x, b->g.blockoffset_y,
+                                           b->g.crop_x, b->g.crop_y, b->g.crop_w, b->g.crop_h, 0);
+        if(crv != MJX_OK) rv = MJ_ERR_UNSUPPORTED_FILETYPE; /* the ordinary path reports it per image */
+    }
+    size_t in_total = 0;
+    if(rv == MJ_OK) {
+        b->ncomp = layout.ncomp;
+        b->image_bytes = 0;
+        for(int c = 0; c < b->ncomp; c++) {
+            const jpeg_component_info *ci = &ref->cinfo.comp_info[c];
+            /* (width_in_blocks / height_in_blocks are set by jpeg_read_header; the arrays libjpeg would allocate are rounded up
+             * to the sampling factors, and so are the planes K5 fills) */
+            b->stride[c] = (int)mjp_virtual_width(ci);
+            b->wreal[c] = (int)ci->width_in_blocks;
+            b->hreal[c] = (int)ci->height_in_blocks;
+            b->vrows[c] = (int)mjp_virtual_height(ci);
+            b->plane_off[c] = b->image_bytes;
+            b->image_bytes += ((size_t)b->stride[c] * (size_t)b->vrows[c] * 128 + 255) & ~(size_t)255;
+        }
+        size_t cap = (b->image_bytes / 4 + 255) & ~(size_t)255;
+        if(cap < 65536) cap = 65536;
+        if(cap > b->image_bytes) cap = b->image_bytes;
+        b->seg_cap = cap;
+        for(int s = 0; s < b->ngroup; s++) {
+            const int i = b->group_buf[s], k = i - b->w0;
+            b->seg_in_off[s] = in_total;
+            in_total += (b->in[i].len - b->ent_off[k] + 255) & ~(size_t)255;
+            if(b->in[i].len - b->ent_off[k] > 0x1ffffff0u) rv = MJ_ERR_UNSUPPORTED_FILETYPE;
+        }
+    }
+    const size_t ng = (size_t)b->ngroup;
+    const size_t tail = sizeof(mjx_image_desc_t) * ng + 8 * ng + 512; /* descriptors, output sizes, K5's verdicts */
+    if(rv == MJ_OK) {
+        void *slab = NULL;
+        int   mrv = mjx_ctx_pinned_scratch(ctx, in_total + tail, &slab);
+        if(mrv == MJX_OK) mrv = dev_grow(ctx, &v->planes, &v->planes_bytes, b->image_bytes * ng);
+        if(mrv == MJX_OK) mrv = dev_grow(ctx, &v->segs, &v->segs_bytes, b->seg_cap * ng);
+        if(mrv == MJX_OK) mrv = dev_grow(ctx, &v->sizes, &v->sizes_bytes, 4 * ng);
+        if(mrv == MJX_OK) mrv = dev_grow(ctx, &v->dstatus, &v->dstatus_bytes, 4 * ng);
+        if(mrv == MJX_OK) mrv = dev_grow(ctx, &v->descs, &v->descs_bytes, sizeof(mjx_image_desc_t) * ng);
+        if(mrv == MJX_OK) mrv = dev_grow(ctx, &v->input, &v->input_bytes, in_total + 256);
+        if(mrv != MJX_OK) rv = MJ_ERR_UNSUPPORTED_FILETYPE; /* no room for the window on the device: the ordinary path */
+        b->slab = (char *)slab;
+    }
+    if(rv != MJ_OK) {
+        for(int k = 0; k < nw; k++) mj_free_jpeg(&b->jp[k]);
+        for(int k = 0; k < nw; k++)
+            if(b->status[b->w0 + k] != MJ_OK && b->in[b->w0 + k].data != NULL) b->status[b->w0 + k] = MJ_OK; /* the full read decides again */
+        return rv;
+    }
+    b->group = b->group_buf;
+    run_phase(b, 8, nthreads, th); /* entropy-coded segments -> page-locked slab */
+
+    mjx_image_desc_t *descs = (mjx_image_desc_t *)(b->slab + in_total);
+    b->seg_size = (unsigned int *)((char *)descs + sizeof(mjx_image_desc_t) * ng);
+    b->dec_status = (uint32_t *)(b->seg_size + ng);
+    memset(descs, 0, sizeof(mjx_image_desc_t) * ng);
+    uint64_t *offs = (uint64_t *)malloc(8 * ng);
+    uint32_t *lens = (uint32_t *)malloc(4 * ng);
+    if(offs == NULL || lens == NULL) {
+        free(offs);
+        free(lens);
+        for(int k = 0; k < nw; k++) mj_free_jpeg(&b->jp[k]);
+        return MJ_ERR_MEMORY;
+    }
+    for(int s = 0; s < b->ngroup; s++) {
+        const int  i = b->group_buf[s], k = i - b->w0;
+        mj_jpeg_t *m = &b->jp[k];
+        offs[s] = (uint64_t)b->seg_in_off[s];
+        lens[s] = (uint32_t)(b->in[i].len - b->ent_off[k]);
+        for(int c = 0; c < b->ncomp; c++) {
+            descs[s].plane[c] = (uint64_t)(uintptr_t)((char *)v->planes + (size_t)s * b->image_bytes + b->plane_off[c]);
+            descs[s].stride_blocks[c] = b->stride[c];
+            descs[s].rows[c] = b->vrows[c];
+            descs[s].wreal[c] = b->wreal[c];
+            descs[s].hreal[c] = b->hreal[c];
+            memcpy(descs[s].q[c], m->cinfo.quant_tbl_ptrs[m->cinfo.comp_info[c].quant_tbl_no]->quantval, 128);
+        }
+    }
+    int mrv = mjx_copy_h2d(ctx, v->input, b->slab, in_total);
+    if(mrv == MJX_OK) mrv = mjx_copy_h2d(ctx, v->descs, descs, sizeof(mjx_image_desc_t) * ng);
+    if(mrv == MJX_OK) mrv = mjx_huffman_decode_batch_device(ctx, v->input, offs, lens, b->ngroup, &b->in_scan[ref_k], (const mjx_image_desc_t *)v->descs, (uint32_t *)v->dstatus);
+    if(mrv == MJX_OK) mrv = mjx_compose_batch_device(ctx, (const mjx_image_desc_t *)v->descs, b->ngroup, *cd, b->g.block_x, b->g.block_y);
+    if(mrv == MJX_OK) mrv = mjx_huffman_encode_batch_device(ctx, (const mjx_image_desc_t *)v->descs, b->ngroup, &out_scan, v->segs, b->seg_cap, (uint32_t *)v->sizes);
+    if(mrv == MJX_OK) mrv = mjx_copy_d2h(ctx, (void *)b->seg_size, v->sizes, 4 * ng);
+    if(mrv == MJX_OK) mrv = mjx_copy_d2h(ctx, (void *)b->dec_status, v->dstatus, 4 * ng);
+    free(offs);
+    free(lens);
+    if(mrv != MJX_OK) {
+        mjx_ctx_sync(ctx);
+        fprintf(stderr, "libmodjpeg (B200): device batch failed: %s\n", mjx_ctx_last_error(ctx));
+        for(int k = 0; k < nw; k++) mj_free_jpeg(&b->jp[k]);
+        return mjp_map_error(mrv);
+    }
+    b->full = 1;
+    return MJ_OK;
+}
+
+static void window_finish_full(batch_t *b, mjx_ctx *ctx, devbufs_t *v, mj_dropon_t *d, unsigned int align, int offset_x, int offset_y, int nthreads,
+                               pthread_t *th) {
+    const double tw = now_s();
+    int          rv = mjx_ctx_sync(ctx);
+    /* output segments, packed into the slab (the input segments there have been uploaded) */
+    size_t at = 0;
+    for(int s = 0; rv == MJX_OK && s < b->ngroup; s++) {
+        unsigned int *sz = (unsigned int *)&b->seg_size[s];
+        if(b->dec_status[s] != 0u) *sz = 0xFFFFFFFFu; /* not decoded: whatever was coded from its planes is void */
+        if(*sz == 0xFFFFFFFFu) continue;
+        b->seg_in_off[s] = at; /* (reused: where the slot's OUTPUT segment lies) */
+        at += ((size_t)*sz + 15) & ~(size_t)15;
+    }
+    if(rv == MJX_OK) {
+        /* descriptors / sizes / verdicts live behind the input segments: keep them clear of the output */
+        const size_t room = (size_t)((const char *)b->seg_size - b->slab) - sizeof(mjx_image_desc_t) * (size_t)b->ngroup;
+        char        *dst = b->slab;
+        void        *big = NULL;
+        if(at > room) { /* more output than input (a large dropon over small files): a slab of its own */
+            big = malloc(at);
+            if(big == NULL) rv = MJX_ERR_MEMORY;
+            dst = (char *)big;
+        }
+        for(int s = 0; rv == MJX_OK && s < b->ngroup; s++)
+            if(b->seg_size[s] != 0xFFFFFFFFu) rv = mjx_copy_d2h(ctx, dst + b->seg_in_off[s], (char *)v->segs + (size_t)s * b->seg_cap, b->seg_size[s]);
+        if(rv == MJX_OK) rv = mjx_ctx_sync(ctx);
+        b->phase_s[0] += now_s() - tw;
+        if(rv == MJX_OK) {
+            char *keep = b->slab;
+            b->slab = dst;
+            b->out_by_offset = 1;
+            run_phase(b, 6, nthreads, th); /* files */
+            b->out_by_offset = 0;
+            b->slab = keep;
+        }
+        free(big);
+    }
+    if(rv != MJX_OK) {
+        fprintf(stderr, "libmodjpeg (B200): device batch failed: %s\n", mjx_ctx_last_error(ctx));
+        for(int s = 0; s < b->ngroup; s++)
+            if(b->status[b->group[s]] == MJ_OK && !b->written[b->group[s] - b->w0]) b->status[b->group[s]] = mjp_map_error(rv);
+    }
+    /* what the device handed back: the ordinary calls, one image at a time */
+    for(int s = 0; s < b->ngroup; s++) {
+        const int i = b->group[s], k = i - b->w0;
+        if(b->status[i] != MJ_OK || b->written[k]) continue;
+        if(rv != MJX_OK) continue;
+        mj_jpeg_t m;
+        mj_init_jpeg(&m);
+        int r2 = mj_read_jpeg_from_memory(&m, b->in[i].data, b->in[i].len, 0);
+        if(r2 == MJ_OK) r2 = mj_compose(&m, d, align, offset_x, offset_y);
+        if(r2 == MJ_OK) r2 = mj_write_jpeg_to_memory(&m, &b->out[i].data, &b->out[i].len, 0);
+        mj_free_jpeg(&m);
+        b->status[i] = r2;
+        if(r2 == MJ_OK) b->written[k] = 1;
+    }
+    for(int k = 0; k < b->w1 - b->w0; k++) mj_free_jpeg(&b->jp[k]);
+    b->full = 0;
+}
+
 /* the pipeline on the calling thread's device */
 static int batch_on_device(int n, const mj_blob_t *in, mj_blob_t *out, int *status, mj_dropon_t *d, unsigned int align, int offset_x,
                            int offset_y, int write_options, int nthreads) {
     const int compose = d->blend != MJ_BLEND_NONE && d->image != NULL && d->alpha != NULL;
-    mjx_ctx  *ctx = compose ? mjx_host_ctx() : NULL;
+    const double t_call = now_s();
+    mjx_ctx     *ctx = compose ? mjx_host_ctx() : NULL;
     if(compose && ctx == NULL) return MJ_ERR_DEVICE;
 
+    /* a plain baseline file wanted (and MJX_GPU_HUFFMAN not 0): planes, blend and entropy coding of a group stay on the device;
+     * and unless MJX_GPU_DECODE=0, windows the device can also DEcode never leave it (window_enqueue_full) */
+    const int on_device = compose && write_options == 0 && mjp_gpu_huffman_mode() != 0;
+    int       full_mode = on_device;
+    {
+        const char *e = getenv("MJX_GPU_DECODE");
+        if(e != NULL && *e == '0') full_mode = 0;
+    }
     int window = 4 * nthreads;
+    if(full_mode && window < 256) window = 256; /* one CTA per image decodes: the device wants a few hundred images at a time */
     if(window > 256) window = 256;
     if(window > n) window = n;
     /* two window states: while the device works on one window (queued by group_enqueue), the pool decodes the next */
@@ -343,13 +587,17 @@ static int batch_on_device(int n, const mj_blob_t *in, mj_blob_t *out, int *stat
         b->jp = (mj_jpeg_t *)calloc((size_t)window, sizeof(mj_jpeg_t));
         b->group_buf = (int *)malloc(sizeof(int) * (size_t)window);
         b->written = (char *)calloc((size_t)window, 1);
-        if(b->jp == NULL || b->group_buf == NULL || b->written == NULL) result = MJ_ERR_MEMORY;
+        b->ent_off = (size_t *)malloc(sizeof(size_t) * (size_t)window);
+        b->seg_in_off = (size_t *)malloc(sizeof(size_t) * (size_t)window);
+        b->eligible = (char *)calloc((size_t)window, 1);
+        b->in_scan = full_mode ? (mjx_scan_t *)malloc(sizeof(mjx_scan_t) * (size_t)window) : NULL;
+        if(b->jp == NULL || b->group_buf == NULL || b->written == NULL || b->ent_off == NULL || b->seg_in_off == NULL || b->eligible == NULL ||
+           (full_mode && b->in_scan == NULL))
+            result = MJ_ERR_MEMORY;
     }
     char      *done = (char *)malloc((size_t)window);
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
     mjx_host_image_t *items = (mjx_host_image_t *)malloc(sizeof(mjx_host_image_t) * (size_t)window);
-    /* a plain baseline file wanted (and MJX_GPU_HUFFMAN not 0): planes, blend and entropy coding of a group stay on the device */
-    const int      on_device = compose && write_options == 0 && mjp_gpu_huffman_mode() != 0;
     devbufs_t      dv;
     mjx_dropon    *cd = NULL;
     mjx_layout_t   cd_layout;
@@ -369,10 +617,31 @@ static int batch_on_device(int n, const mj_blob_t *in, mj_blob_t *out, int *stat
         bp->w0 = w0;
         bp->w1 = w0 + window < n ? w0 + window : n;
         w0 = bp->w1;
+        if(full_mode) {
+            run_phase(bp, 7, nthreads, th); /* markers only -- the device works on the pending window meanwhile */
+            if(pending != NULL) {
+                if(pending->full) window_finish_full(pending, ctx, &dv, d, align, offset_x, offset_y, nthreads, th);
+                else {
+                    group_finish(pending, ctx, &dv, nthreads, th);
+                    run_phase(pending, 4, nthreads, th);
+                }
+                pending = NULL;
+            }
+            memset(bp->written, 0, (size_t)window);
+            if(window_enqueue_full(bp, ctx, &dv, &cd, &cd_layout, &cd_g, d, align, offset_x, offset_y, nthreads, th) == MJ_OK) {
+                pending = bp;
+                cur ^= 1;
+                continue;
+            }
+            /* not a window of that kind: read it in full */
+        }
         run_phase(bp, 1, nthreads, th); /* entropy decode -- the device works on the pending window meanwhile */
         if(pending != NULL) {
-            group_finish(pending, ctx, &dv, nthreads, th);
-            run_phase(pending, 4, nthreads, th); /* free; host encode of what the device handed back */
+            if(pending->full) window_finish_full(pending, ctx, &dv, d, align, offset_x, offset_y, nthreads, th);
+            else {
+                group_finish(pending, ctx, &dv, nthreads, th);
+                run_phase(pending, 4, nthreads, th); /* free; host encode of what the device handed back */
+            }
             pending = NULL;
         }
 
@@ -474,15 +743,18 @@ static int batch_on_device(int n, const mj_blob_t *in, mj_blob_t *out, int *stat
         else run_phase(bp, 4, nthreads, th); /* entropy encode + free */
     }
     if(pending != NULL) {
-        group_finish(pending, ctx, &dv, nthreads, th);
-        run_phase(pending, 4, nthreads, th);
+        if(pending->full) window_finish_full(pending, ctx, &dv, d, align, offset_x, offset_y, nthreads, th);
+        else {
+            group_finish(pending, ctx, &dv, nthreads, th);
+            run_phase(pending, 4, nthreads, th);
+        }
         pending = NULL;
     }
     if(getenv("MJ_BATCH_TRACE") != NULL) {
-        double ps[7];
-        for(int k = 0; k < 7; k++) ps[k] = B[0].phase_s[k] + B[1].phase_s[k];
-        fprintf(stderr, "mj_compose_batch: %d images, %d threads: decode %.3f s, stage-in %.3f s, %s %.3f s, stage-out %.3f s, %s %.3f s\n", n,
-                nthreads, ps[1], ps[2] + ps[5], on_device ? "waited for the device (copies + K2 + K4 not hidden by the next decode)" : "K2", ps[0], ps[3],
+        double ps[9];
+        for(int k = 0; k < 9; k++) ps[k] = B[0].phase_s[k] + B[1].phase_s[k];
+        fprintf(stderr, "mj_compose_batch: %d images, %d threads, %.3f s: headers %.3f s, decode %.3f s, stage-in %.3f s, %s %.3f s, stage-out %.3f s, %s %.3f s\n", n,
+                nthreads, now_s() - t_call, ps[7], ps[1], ps[2] + ps[5] + ps[8], on_device ? "waited for the device (copies + K2 + K4 not hidden by the next decode)" : "K2", ps[0], ps[3],
                 on_device ? "files (markers + segment) + host encode" : "encode", ps[4] + ps[6]);
     }
 out:
@@ -495,6 +767,10 @@ out:
         free(B[k].jp);
         free(B[k].group_buf);
         free(B[k].written);
+        free(B[k].ent_off);
+        free(B[k].seg_in_off);
+        free(B[k].eligible);
+        free(B[k].in_scan);
         pthread_mutex_destroy(&B[k].lock);
     }
     free(done);

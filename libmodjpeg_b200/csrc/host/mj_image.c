@@ -22,6 +22,8 @@ void mj_free_jpeg(mj_jpeg_t *m) {
 
 mjp_trap_t *mjp_image_trap(mj_jpeg_t *m) { return (mjp_trap_t *)m->cinfo.err; }
 
+static void copy_table(mjx_huff_table_t *dst, const JHUFF_TBL *src);
+
 int mj_read_jpeg_from_memory(mj_jpeg_t *m, const unsigned char *memory, size_t len, size_t max_pixel) {
     if(m == NULL || memory == NULL || len == 0) return MJ_ERR_NULL_DATA;
 
@@ -85,6 +87,106 @@ int mj_read_jpeg_from_memory(mj_jpeg_t *m, const unsigned char *memory, size_t l
         s->samp_factor[c].v_samp_factor = m->cinfo.comp_info[c].v_samp_factor;
     }
     /* all input has been consumed: the caller may release `memory` now */
+    src->data = NULL;
+    src->size = 0;
+    trap->armed = 0;
+    return MJ_OK;
+}
+
+/* Read the markers of a JPEG up to its first scan and stop: m holds the frame (size, sampling, quantisation tables, saved
+ * markers) but no coefficients (m->coef == NULL).  For files whose ONE scan the device can decode (k5_huffman_decode.cu):
+ * 8-bit sequential Huffman, every component in the scan, no restart markers.  *entropy_off = where the entropy-coded segment
+ * starts in `memory`; *scan = that scan with the FILE's tables.  MJ_ERR_UNSUPPORTED_FILETYPE: a valid file of another kind
+ * (the caller reads it with mj_read_jpeg_from_memory); other codes as mj_read_jpeg_from_memory. */
+int mjp_read_header_only(mj_jpeg_t *m, const unsigned char *memory, size_t len, size_t *entropy_off, mjx_scan_t *scan) {
+    if(m == NULL || memory == NULL || len == 0) return MJ_ERR_NULL_DATA;
+    mj_free_jpeg(m);
+    mjp_trap_t boot;
+    mjp_trap_init(&boot);
+    m->cinfo.err = &boot.base;
+    boot.armed = 1;
+    if(setjmp(boot.escape)) {
+        jpeg_destroy_decompress(&m->cinfo);
+        mj_init_jpeg(m);
+        return MJ_ERR_DECODE_JPEG;
+    }
+    jpeg_create_decompress(&m->cinfo);
+    mjp_trap_t   *trap = (mjp_trap_t *)(*m->cinfo.mem->alloc_small)((j_common_ptr)&m->cinfo, JPOOL_PERMANENT, sizeof(mjp_trap_t));
+    mjp_memsrc_t *src = (mjp_memsrc_t *)(*m->cinfo.mem->alloc_small)((j_common_ptr)&m->cinfo, JPOOL_PERMANENT, sizeof(mjp_memsrc_t));
+    mjp_trap_init(trap);
+    m->cinfo.err = &trap->base;
+    trap->armed = 1;
+    if(setjmp(trap->escape)) {
+        jpeg_destroy_decompress(&m->cinfo);
+        mj_init_jpeg(m);
+        return MJ_ERR_DECODE_JPEG;
+    }
+    mjp_memsrc_init(src, memory, len);
+    m->cinfo.src = &src->base;
+    jpeg_save_markers(&m->cinfo, JPEG_COM, 0xFFFF);
+    for(int k = 0; k < 16; k++) jpeg_save_markers(&m->cinfo, JPEG_APP0 + k, 0xFFFF);
+    jpeg_read_header(&m->cinfo, TRUE); /* stops behind the header of the first scan */
+    m->width = (int)m->cinfo.image_width;
+    m->height = (int)m->cinfo.image_height;
+
+    int                     rv = MJ_OK;
+    const j_decompress_ptr  ci = &m->cinfo;
+    const int               nc = ci->num_components;
+    if(ci->jpeg_color_space != JCS_GRAYSCALE && ci->jpeg_color_space != JCS_RGB && ci->jpeg_color_space != JCS_YCbCr) rv = MJ_ERR_UNSUPPORTED_COLORSPACE;
+    else if(ci->progressive_mode || ci->arith_code || ci->data_precision != 8 || ci->restart_interval != 0 || nc < 1 || nc > MJX_MAX_COMPONENTS ||
+            ci->comps_in_scan != nc || ci->Ss != 0 || ci->Se != DCTSIZE2 - 1 || ci->Ah != 0 || ci->Al != 0)
+        rv = MJ_ERR_UNSUPPORTED_FILETYPE;
+    if(rv == MJ_OK) {
+        memset(scan, 0, sizeof(*scan));
+        scan->ncomp = nc;
+        int blocks = 0;
+        for(int c = 0; c < nc && rv == MJ_OK; c++) {
+            const jpeg_component_info *cc = ci->cur_comp_info[c];
+            if(cc != &ci->comp_info[c] || ci->quant_tbl_ptrs[cc->quant_tbl_no] == NULL) rv = MJ_ERR_UNSUPPORTED_FILETYPE; /* scan order = frame order */
+            else {
+                scan->h_samp[c] = cc->h_samp_factor;
+                scan->v_samp[c] = cc->v_samp_factor;
+                scan->dc_tbl[c] = cc->dc_tbl_no;
+                scan->ac_tbl[c] = cc->ac_tbl_no;
+                blocks += cc->h_samp_factor * cc->v_samp_factor;
+                if(cc->dc_tbl_no < 0 || cc->dc_tbl_no > 3 || cc->ac_tbl_no < 0 || cc->ac_tbl_no > 3 || ci->dc_huff_tbl_ptrs[cc->dc_tbl_no] == NULL ||
+                   ci->ac_huff_tbl_ptrs[cc->ac_tbl_no] == NULL)
+                    rv = MJ_ERR_UNSUPPORTED_FILETYPE;
+            }
+        }
+        if(nc > 1 && blocks > 10) rv = MJ_ERR_UNSUPPORTED_FILETYPE;
+        for(int i = 0; i < 4 && rv == MJ_OK; i++) {
+            copy_table(&scan->dc[i], ci->dc_huff_tbl_ptrs[i]);
+            copy_table(&scan->ac[i], ci->ac_huff_tbl_ptrs[i]);
+        }
+        if(rv == MJ_OK) {
+            if(nc == 1) { /* not interleaved: the component's own grid of blocks (jdinput.c per_scan_setup) */
+                const long hs = ci->comp_info[0].h_samp_factor, vs = ci->comp_info[0].v_samp_factor;
+                scan->mcus_per_row = (int)(((long)ci->image_width * hs + ci->max_h_samp_factor * DCTSIZE - 1) / (ci->max_h_samp_factor * DCTSIZE));
+                scan->mcu_rows = (int)(((long)ci->image_height * vs + ci->max_v_samp_factor * DCTSIZE - 1) / (ci->max_v_samp_factor * DCTSIZE));
+            }
+            else {
+                const long mw = (long)ci->max_h_samp_factor * DCTSIZE, mh = (long)ci->max_v_samp_factor * DCTSIZE;
+                scan->mcus_per_row = (int)(((long)ci->image_width + mw - 1) / mw);
+                scan->mcu_rows = (int)(((long)ci->image_height + mh - 1) / mh);
+            }
+            *entropy_off = (size_t)(src->base.next_input_byte - memory);
+        }
+    }
+    if(rv != MJ_OK) {
+        jpeg_destroy_decompress(&m->cinfo);
+        mj_init_jpeg(m);
+        return rv;
+    }
+    mj_sampling_t *sp = &m->sampling;
+    sp->max_h_samp_factor = ci->max_h_samp_factor;
+    sp->max_v_samp_factor = ci->max_v_samp_factor;
+    sp->h_factor = sp->max_h_samp_factor * DCTSIZE;
+    sp->v_factor = sp->max_v_samp_factor * DCTSIZE;
+    for(int c = 0; c < nc && c < 4; c++) {
+        sp->samp_factor[c].h_samp_factor = ci->comp_info[c].h_samp_factor;
+        sp->samp_factor[c].v_samp_factor = ci->comp_info[c].v_samp_factor;
+    }
     src->data = NULL;
     src->size = 0;
     trap->armed = 0;
@@ -188,7 +290,12 @@ int mjp_scan_headers(mj_jpeg_t *m, unsigned char **head, size_t *head_len, mjx_s
         }
     }
 
-    jpeg_write_coefficients(&out, m->coef);
+    {
+        /* An image of which only the header was read (mjp_read_header_only) has no coefficient arrays; libjpeg only stores the
+         * pointer here and would first look at the arrays when it codes a row of blocks -- which it never gets to. */
+        static jvirt_barray_ptr no_arrays[MAX_COMPONENTS];
+        jpeg_write_coefficients(&out, m->coef != NULL ? m->coef : no_arrays);
+    }
     for(jpeg_saved_marker_ptr mk = m->cinfo.marker_list; mk != NULL; mk = mk->next)
         jpeg_write_marker(&out, mk->marker, mk->data, mk->data_length);
     memset(&stop, 0, sizeof(stop));
@@ -391,6 +498,11 @@ int mjx_jpeg_qtable(mj_jpeg_t *m, int c, unsigned short *q64) {
 
 int mjx_jpeg_layout(mj_jpeg_t *m, mjx_layout_t *layout) {
     if(m == NULL || m->coef == NULL || layout == NULL) return MJ_ERR_NULL_DATA;
+    return mjp_layout_of(m, layout);
+}
+
+/* (also for an image of which only the header has been read, mjp_read_header_only) */
+int mjp_layout_of(mj_jpeg_t *m, mjx_layout_t *layout) {
     memset(layout, 0, sizeof(*layout));
     layout->colorspace = (int)m->cinfo.jpeg_color_space;
     layout->ncomp = m->cinfo.num_components;

@@ -70,6 +70,9 @@ int mjp_gpu_huffman_mode(void); /* -1 unset, 0 off, 1 on */
 int mjp_scan_headers(mj_jpeg_t *m, unsigned char **head, size_t *head_len, mjx_scan_t *scan);
 int mjp_assemble_file(unsigned char **memory, size_t *len, const unsigned char *head, size_t head_len, const unsigned char *seg, size_t seg_len);
 
+int mjp_read_header_only(mj_jpeg_t *m, const unsigned char *memory, size_t len, size_t *entropy_off, mjx_scan_t *scan);
+int mjp_layout_of(mj_jpeg_t *m, mjx_layout_t *layout);
+
 /* MJX_* -> MJ_* */
 int mjp_map_error(int mjx_rv);
 

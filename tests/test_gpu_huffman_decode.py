@@ -115,3 +115,26 @@ def test_corrupt_stream_is_handed_back(engine):
     finally:
         engine.device_free(data_dev)
         engine.device_free(status_dev)
+
+
+def test_compose_batch_window_never_leaves_the_device(engine):
+    """mj_compose_batch on a window of one geometry: JPEG bytes up, K5 -> K2 -> K4 in HBM, JPEG bytes back -- the files equal
+    read -> mj_compose -> write through the per-image API (host libjpeg on both ends), byte for byte"""
+    raw = util.logo_rgba(200, 120, tile=64, radius=27)
+    d = M.Dropon()
+    assert d.read_dropon_from_raw(raw, M.CS_RGBA, 255) == 0
+    jpegs = [util.jpeg_bytes(333, 250, "420", 70 + (i % 3) * 10, seed=500 + i) for i in range(37)]
+    jpegs[11] = b"definitely not a jpeg"
+    rv, status, outs = capi.compose_batch(jpegs, d, M.ALIGN_BOTTOM | M.ALIGN_RIGHT, -9, -6, 0, nthreads=4)
+    assert rv == 0
+    for k, src in enumerate(jpegs):
+        if k == 11:
+            assert status[k] == 5 and outs[k] is None
+            continue
+        assert status[k] == 0, k
+        j = M.Jpeg()
+        assert j.read_jpeg_from_memory(src) == 0
+        assert j.compose(d, M.ALIGN_BOTTOM | M.ALIGN_RIGHT, -9, -6) == 0
+        rvw, want = j.write_jpeg_to_memory(0)
+        assert rvw == 0
+        assert outs[k] == want, k
