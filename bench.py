@@ -801,9 +801,12 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
         if rank == 0:
             files = {"images": args.file_images * world, "threads_per_rank": threads, "ranks": world, "images_per_s": args.file_images * world / tf,
                      "mblocks_per_s": args.file_images * world * blocks_per_image / tf / 1e6,
-                     "path": ("mj_compose_batch per rank: libjpeg entropy decode (thread pool) -> K1 once -> whole planes of a window to HBM -> K2 -> "
+                     "path": ("mj_compose_batch per rank: markers read by libjpeg (thread pool) -> entropy-coded segments of a window to HBM -> K5 Huffman "
+                              "decoding -> K1 once -> K2 -> K4 Huffman coding -> entropy-coded segments back, libjpeg's markers in front (thread pool); "
+                              "JPEG bytes in, JPEG bytes out" if os.environ.get("MJX_GPU_HUFFMAN", "") != "0" and os.environ.get("MJX_GPU_DECODE", "") != "0" else
+                              "mj_compose_batch per rank: libjpeg entropy decode (thread pool) -> K1 once -> whole planes of a window to HBM -> K2 -> "
                               "K4 Huffman coding on the device -> entropy-coded segments back, libjpeg's markers in front (thread pool); "
-                              "JPEG bytes in, JPEG bytes out" if os.environ.get("MJX_GPU_HUFFMAN", "") != "0" else
+                              "JPEG bytes in, JPEG bytes out (MJX_GPU_DECODE=0)" if os.environ.get("MJX_GPU_HUFFMAN", "") != "0" else
                               "mj_compose_batch per rank: libjpeg entropy decode (thread pool) -> K1 once -> K2 one launch per window, zero-copy "
                               "on a page-locked slab -> libjpeg entropy encode (thread pool); JPEG bytes in, JPEG bytes out (MJX_GPU_HUFFMAN=0)"),
                      "bytes_in": sum(len(b) for b in batch) * world, "bytes_out": sum(len(o) for o in outs) * world}
