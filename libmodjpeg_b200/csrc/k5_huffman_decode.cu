@@ -24,6 +24,7 @@
 // planes' padding exactly as libjpeg does, so the planes equal jpeg_read_coefficients' arrays block for block.
 // status[i] != 0: not decoded (a code the tables do not contain, a run past coefficient 63, fewer blocks than the frame
 // announces) -- the caller lets libjpeg read that image (and report its error).
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -461,6 +462,16 @@ int mjx_huffman_decode_batch_device(mjx_ctx *ctx, const void *data_dev, const ui
     ctx->launches += 1;
     const cudaError_t e = cudaGetLastError();
     if(e != cudaSuccess) return fail(ctx, e, "k5_decode_kernel");
+    if(getenv("MJX_K5_TRACE") != nullptr) { // diagnostics: how many rounds the entry states needed (synchronises the stream)
+        uint32_t *r = (uint32_t *)malloc((size_t)n * 4);
+        if(r && cudaMemcpyAsync(r, p.rounds, (size_t)n * 4, cudaMemcpyDeviceToHost, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess) {
+            unsigned long long sum = 0;
+            uint32_t           mx = 0;
+            for(int i = 0; i < n; i++) sum += r[i], mx = r[i] > mx ? r[i] : mx;
+            fprintf(stderr, "k5_decode_kernel: %d images, at most %u bytes each: rounds mean %.1f, max %u\n", n, maxlen, (double)sum / n, mx);
+        }
+        free(r);
+    }
     return MJX_OK;
 }
 

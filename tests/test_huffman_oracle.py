@@ -71,3 +71,29 @@ def test_oracle_refuses_what_libjpeg_refuses(built):
     # (classic libjpeg raises JERR_BAD_DCT_COEF here; libjpeg-turbo's encoder does not check and writes an undecodable
     # stream -- either way the GPU encoder must not be the one to code this block: it hands the image back, see
     # tests/test_gpu_huffman.py::test_uncodable_coefficient_falls_back_to_libjpeg)
+
+
+def test_marker_parser_agrees_with_libjpeg(built):
+    """capi.scan_from_jpeg (what a batch host hands to K5): tables, sampling, MCU grid and the start of the entropy-coded
+    segment of files libjpeg wrote"""
+    for (w, h, subs, gray, quality) in CASES:
+        data = util.jpeg_bytes(w, h, subs, quality, seed=w, gray=gray)
+        scan, off, frame = capi.scan_from_jpeg(data)
+        head, seg, tail = H.split_jpeg(data)
+        assert off == len(head) and frame["width"] == w and frame["height"] == h
+        j = M.Jpeg()
+        assert j.read_jpeg_from_memory(data) == 0
+        ref = capi.standard_scan(w, h, j.sampling())
+        # Pillow writes the Annex K tables unless asked to optimise -- the ones the components use (a grayscale file has no chroma tables)
+        assert (scan.ncomp, scan.mcus_per_row, scan.mcu_rows) == (ref.ncomp, ref.mcus_per_row, ref.mcu_rows)
+        for c in range(scan.ncomp):
+            assert (scan.h_samp[c], scan.v_samp[c], scan.dc_tbl[c], scan.ac_tbl[c]) == (ref.h_samp[c], ref.v_samp[c], ref.dc_tbl[c], ref.ac_tbl[c])
+            assert bytes(scan.dc[scan.dc_tbl[c]]) == bytes(ref.dc[ref.dc_tbl[c]]) and bytes(scan.ac[scan.ac_tbl[c]]) == bytes(ref.ac[ref.ac_tbl[c]])
+    with pytest.raises(ValueError):
+        import io
+
+        from PIL import Image
+
+        buf = io.BytesIO()
+        Image.fromarray(util.photo(64, 64, 1)).save(buf, "JPEG", progressive=True)
+        capi.scan_from_jpeg(buf.getvalue())
