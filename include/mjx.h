@@ -147,6 +147,9 @@ int  mjx_host_alloc(mjx_ctx *ctx, void **ptr, size_t bytes); /* page-locked */
 void mjx_host_free(mjx_ctx *ctx, void *ptr);
 /* a grow-only page-locked scratch buffer owned by the ctx (valid until the next call that asks for more, or destroy) */
 int  mjx_ctx_pinned_scratch(mjx_ctx *ctx, size_t bytes, void **ptr);
+/* the same in device memory: one grow-only buffer owned by the ctx (freed with it); growing waits for the ctx's streams and
+ * loses the contents */
+int  mjx_ctx_device_scratch(mjx_ctx *ctx, size_t bytes, void **ptr);
 int  mjx_copy_h2d(mjx_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes); /* async on the ctx stream */
 int  mjx_copy_d2h(mjx_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
 

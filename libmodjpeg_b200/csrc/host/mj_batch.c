@@ -228,28 +228,24 @@ static int same_geometry(const mj_jpeg_t *a, const mj_jpeg_t *b) {
 
 /* Device buffers of the device-resident path, kept across groups and windows */
 typedef struct {
-    void  *planes, *segs, *sizes, *descs, *input, *dstatus;
-    size_t planes_bytes, segs_bytes, sizes_bytes, descs_bytes, input_bytes, dstatus_bytes;
+    void *planes, *segs, *sizes, *descs, *input, *dstatus;
 } devbufs_t;
 
-static int dev_grow(mjx_ctx *ctx, void **p, size_t *have, size_t want) {
-    if(*have >= want) return MJX_OK;
-    if(*p) mjx_device_free(ctx, *p);
-    *p = NULL;
-    *have = 0;
-    int rv = mjx_device_alloc(ctx, p, want + want / 8);
-    if(rv == MJX_OK) *have = want + want / 8;
-    return rv;
-}
-
-static void dev_release(mjx_ctx *ctx, devbufs_t *v) {
-    if(v->planes) mjx_device_free(ctx, v->planes);
-    if(v->segs) mjx_device_free(ctx, v->segs);
-    if(v->sizes) mjx_device_free(ctx, v->sizes);
-    if(v->descs) mjx_device_free(ctx, v->descs);
-    if(v->input) mjx_device_free(ctx, v->input);
-    if(v->dstatus) mjx_device_free(ctx, v->dstatus);
-    memset(v, 0, sizeof(*v));
+/* the device buffers of a window: one ctx-owned, grow-only scratch (it outlives the call: a server that sends batch after batch
+ * allocates once), cut into the pieces a window needs */
+static int dev_layout(mjx_ctx *ctx, devbufs_t *v, size_t planes, size_t segs, size_t sizes, size_t descs, size_t input, size_t dstatus) {
+    const size_t need[6] = {planes, segs, sizes, descs, input, dstatus};
+    size_t       off[6], total = 0;
+    for(int k = 0; k < 6; k++) {
+        off[k] = total;
+        total += (need[k] + 255) & ~(size_t)255;
+    }
+    void *base = NULL;
+    int   rv = mjx_ctx_device_scratch(ctx, total, &base);
+    if(rv != MJX_OK) return rv;
+    v->planes = (char *)base + off[0], v->segs = (char *)base + off[1], v->sizes = (char *)base + off[2];
+    v->descs = (char *)base + off[3], v->input = (char *)base + off[4], v->dstatus = (char *)base + off[5];
+    return MJX_OK;
 }
 
 /* One group (images of one geometry) entirely on the device: whole planes up, K2 in HBM, K4 codes the scans, only the
@@ -288,10 +284,7 @@ static int group_enqueue(batch_t *b, mjx_ctx *ctx, devbufs_t *v, mjx_dropon *cd,
     void        *slab = NULL;
     /* slab: the images' regions, then the descriptors, then the segment sizes the device reports */
     int rv = mjx_ctx_pinned_scratch(ctx, b->image_bytes * ng + sizeof(mjx_image_desc_t) * ng + 4 * ng + 256, &slab);
-    if(rv == MJX_OK) rv = dev_grow(ctx, &v->planes, &v->planes_bytes, b->image_bytes * ng);
-    if(rv == MJX_OK) rv = dev_grow(ctx, &v->segs, &v->segs_bytes, cap * ng);
-    if(rv == MJX_OK) rv = dev_grow(ctx, &v->sizes, &v->sizes_bytes, 4 * ng);
-    if(rv == MJX_OK) rv = dev_grow(ctx, &v->descs, &v->descs_bytes, sizeof(mjx_image_desc_t) * ng);
+    if(rv == MJX_OK) rv = dev_layout(ctx, v, b->image_bytes * ng, cap * ng, 4 * ng, sizeof(mjx_image_desc_t) * ng, 0, 0);
     if(rv != MJX_OK) return mjp_map_error(rv);
     b->slab = (char *)slab;
     run_phase(b, 5, nthreads, th); /* whole planes -> page-locked slab */
@@ -433,12 +426,7 @@ static int window_enqueue_full(batch_t *b, mjx_ctx *ctx, devbufs_t *v, mjx_dropo
     if(rv == MJ_OK) {
         void *slab = NULL;
         int   mrv = mjx_ctx_pinned_scratch(ctx, in_total + tail, &slab);
-        if(mrv == MJX_OK) mrv = dev_grow(ctx, &v->planes, &v->planes_bytes, b->image_bytes * ng);
-        if(mrv == MJX_OK) mrv = dev_grow(ctx, &v->segs, &v->segs_bytes, b->seg_cap * ng);
-        if(mrv == MJX_OK) mrv = dev_grow(ctx, &v->sizes, &v->sizes_bytes, 4 * ng);
-        if(mrv == MJX_OK) mrv = dev_grow(ctx, &v->dstatus, &v->dstatus_bytes, 4 * ng);
-        if(mrv == MJX_OK) mrv = dev_grow(ctx, &v->descs, &v->descs_bytes, sizeof(mjx_image_desc_t) * ng);
-        if(mrv == MJX_OK) mrv = dev_grow(ctx, &v->input, &v->input_bytes, in_total + 256);
+        if(mrv == MJX_OK) mrv = dev_layout(ctx, v, b->image_bytes * ng, b->seg_cap * ng, 4 * ng, sizeof(mjx_image_desc_t) * ng, in_total + 256, 4 * ng);
         if(mrv != MJX_OK) rv = MJ_ERR_UNSUPPORTED_FILETYPE; /* no room for the window on the device: the ordinary path */
         b->slab = (char *)slab;
     }
@@ -758,10 +746,7 @@ static int batch_on_device(int n, const mj_blob_t *in, mj_blob_t *out, int *stat
                 on_device ? "files (markers + segment) + host encode" : "encode", ps[4] + ps[6]);
     }
 out:
-    if(ctx != NULL) {
-        mjx_ctx_sync(ctx);
-        dev_release(ctx, &dv);
-    }
+    if(ctx != NULL) mjx_ctx_sync(ctx);
     if(cd != NULL) mjx_dropon_free(cd);
     for(int k = 0; k < 2; k++) {
         free(B[k].jp);

@@ -132,6 +132,7 @@ void mjx_ctx_destroy(mjx_ctx *ctx) {
     if(ctx->desc_dev) cudaFree(ctx->desc_dev);
     if(ctx->scratch) cudaFree(ctx->scratch);
     if(ctx->huff) cudaFree(ctx->huff);
+    if(ctx->dev2) cudaFree(ctx->dev2);
     if(ctx->side_stream) {
         cudaStreamSynchronize(ctx->side_stream);
         cudaStreamDestroy(ctx->side_stream);
@@ -197,6 +198,15 @@ int mjx_ctx_pinned_scratch(mjx_ctx *ctx, size_t bytes, void **ptr) {
     if(!ptr) return MJX_ERR_ARG;
     if((rv = grow(ctx, &ctx->pin2, &ctx->pin2_bytes, bytes ? bytes : 1, true)) != MJX_OK) return rv;
     *ptr = ctx->pin2;
+    return MJX_OK;
+}
+
+int mjx_ctx_device_scratch(mjx_ctx *ctx, size_t bytes, void **ptr) {
+    int rv = use_device(ctx);
+    if(rv) return rv;
+    if(!ptr) return MJX_ERR_ARG;
+    if((rv = grow(ctx, &ctx->dev2, &ctx->dev2_bytes, bytes ? bytes : 1, false)) != MJX_OK) return rv;
+    *ptr = ctx->dev2;
     return MJX_OK;
 }
 

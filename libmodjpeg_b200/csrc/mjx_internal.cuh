@@ -113,6 +113,8 @@ struct mjx_ctx {
     size_t desc_bytes = 0;
     void  *scratch = nullptr; // per-launch K2 scratch: work counters
     size_t scratch_bytes = 0;
+    void  *dev2 = nullptr;    // caller-visible device scratch (mjx_ctx_device_scratch)
+    size_t dev2_bytes = 0;
     void  *huff = nullptr;    // K4 scratch: block bit lengths, the unstuffed stream, piece counts (k4_huffman.cu)
     size_t huff_bytes = 0;
 

@@ -138,3 +138,38 @@ def test_compose_batch_window_never_leaves_the_device(engine):
         rvw, want = j.write_jpeg_to_memory(0)
         assert rvw == 0
         assert outs[k] == want, k
+
+
+def test_damaged_files_do_not_bring_the_pipeline_down(engine):
+    """bit flips and truncations in the entropy-coded data of a window that takes the device path: every image gets a status
+    and (when it is 0) a file libjpeg can read; the intact neighbours are untouched"""
+    raw = util.logo_rgba(96, 64, 32, 13)
+    d = M.Dropon()
+    assert d.read_dropon_from_raw(raw, M.CS_RGBA, 255) == 0
+    rng = np.random.default_rng(11)
+    good = [util.jpeg_bytes(256, 192, "420", 85, seed=600 + i) for i in range(24)]
+    files = list(good)
+    damaged = set()
+    for i in range(0, 24, 3):
+        b = bytearray(files[i])
+        off = capi.scan_from_jpeg(files[i])[1]
+        if i % 2 == 0:
+            for _ in range(5):
+                b[int(rng.integers(off, len(b) - 2))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            del b[off + (len(b) - off) // 2:]
+            b += b"\xff\xd9"
+        files[i] = bytes(b)
+        damaged.add(i)
+    rv, status, outs = capi.compose_batch(files, d, M.ALIGN_CENTER, 0, 0, 0, nthreads=4)
+    assert rv == 0
+    for i in range(24):
+        if i in damaged:
+            if status[i] == 0:
+                j = M.Jpeg()
+                assert j.read_jpeg_from_memory(outs[i]) == 0
+            continue
+        assert status[i] == 0
+        j = M.Jpeg()
+        assert j.read_jpeg_from_memory(good[i]) == 0 and j.compose(d, M.ALIGN_CENTER, 0, 0) == 0
+        assert j.write_jpeg_to_memory(0)[1] == outs[i], i
