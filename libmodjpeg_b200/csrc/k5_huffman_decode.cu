@@ -11,7 +11,8 @@
 // ICPP 2018, whose scheme this follows).  One CTA per image:
 //   1. un-stuff: every 0x00 behind a 0xFF is dropped (parallel count, CTA-wide prefix sum, scatter), the stream is kept as
 //      big-endian 32-bit words so that a bit window is one funnel shift;
-//   2. the stream is cut into subsequences of kSubBits bits.  entry[t] = decoder state at the start of subsequence t:
+//   2. the stream is cut into subsequences (one per thread where the image is large enough: at least kMinSubBits bits each).
+//      entry[t] = decoder state at the start of subsequence t:
 //      exact for t = 0, a guess (block start of the MCU's first block) for the others.  ROUNDS: every subsequence whose
 //      entry state changed is decoded (no output) and its exit state becomes the entry state of the next one.  When a round
 //      changes nothing, every entry state is exact by induction from t = 0 -- no probabilistic argument is involved, only
@@ -33,7 +34,9 @@
 namespace mjx {
 
 static constexpr int kDecThreads = 1024;
-static constexpr int kSubBits = 1024; // bits per subsequence
+static constexpr int kMinSubBits = 256; // shortest subsequence; larger images: total bits / threads, so that every thread has ONE
+                                        // (the entry states settle in as many rounds as a decoder needs subsequences to synchronise:
+                                        // the longer the subsequence, the fewer rounds -- 1 024-bit pieces took 9 rounds on 1080p files)
 static constexpr int kLook = 9;       // bits of the first-level code lookup
 
 // one Huffman table, ready for decoding (host-built: ITU-T T.81 F.2.2.3 / libjpeg jdhuff.c jpeg_make_d_derived_tbl)
@@ -250,7 +253,8 @@ __global__ void __launch_bounds__(kDecThreads) k5_decode_kernel(const DecParams 
     }
     __syncthreads();
     const uint32_t total_bits = s_total_bits;
-    const uint32_t nsub = (total_bits + kSubBits - 1) / kSubBits;
+    const uint32_t sub_bits = max((uint32_t)kMinSubBits, ((total_bits + kDecThreads - 1) / kDecThreads + 31u) & ~31u);
+    const uint32_t nsub = (total_bits + sub_bits - 1) / sub_bits;
     uint2         *entry = p.entry + (size_t)img * p.sub_stride, *exits = p.exits + (size_t)img * p.sub_stride;
     uint32_t      *cnt = p.cnt + (size_t)img * p.sub_stride;
     unsigned char *dirty = p.dirty + (size_t)img * 2 * p.sub_stride, *next = dirty + p.sub_stride;
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(kDecThreads) k5_decode_kernel(const DecParams 
     // ---- 2. entry states by rounds ----
     for(uint32_t t = tid; t < nsub; t += kDecThreads) {
         DecState s;
-        s.p = t * kSubBits, s.b = 0, s.z = 0, s.bad = 0;
+        s.p = t * sub_bits, s.b = 0, s.z = 0, s.bad = 0;
         entry[t] = pack_state(s);
         dirty[t] = 1;
         next[t] = 0;
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(kDecThreads) k5_decode_kernel(const DecParams 
         for(uint32_t t = tid; t < nsub; t += kDecThreads) {
             if(!dirty[t]) continue;
             DecState s = unpack_state(entry[t]);
-            cnt[t] = decode_run<false>(p, im, s_tab, words, s, min((t + 1) * kSubBits, total_bits), 0u);
+            cnt[t] = decode_run<false>(p, im, s_tab, words, s, min((t + 1) * sub_bits, total_bits), 0u);
             exits[t] = pack_state(s);
         }
         __syncthreads();
@@ -314,7 +318,7 @@ __global__ void __launch_bounds__(kDecThreads) k5_decode_kernel(const DecParams 
         const uint32_t blk = cnt[t];
         if(blk >= (uint32_t)p.nblk) continue; // behind the last block of the frame: padding bits, EOI, whatever follows
         DecState s = unpack_state(entry[t]);
-        const uint32_t done = decode_run<true>(p, im, s_tab, words, s, min((t + 1) * kSubBits, total_bits), blk);
+        const uint32_t done = decode_run<true>(p, im, s_tab, words, s, min((t + 1) * sub_bits, total_bits), blk);
         (void)done;
         if(s.bad) bad = 1;
     }
@@ -423,7 +427,7 @@ int mjx_huffman_decode_batch_device(mjx_ctx *ctx, const void *data_dev, const ui
         if(lengths[i] > maxlen) maxlen = lengths[i];
     }
     // scratch: tables, offsets, lengths, rounds, then per image the word stream and the subsequence arrays
-    const size_t words_stride = ((size_t)maxlen + 3) / 4 + 8, sub_stride = (((size_t)maxlen * 8 + kSubBits - 1) / kSubBits + 8 + 3) & ~(size_t)3;
+    const size_t words_stride = ((size_t)maxlen + 3) / 4 + 8, sub_stride = kDecThreads + 8; // at most one subsequence per thread
     size_t       off = 0;
     auto         take = [&](size_t b) {
         const size_t o = off;
