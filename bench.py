@@ -789,7 +789,7 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
         d = M.Dropon()
         assert d.read_dropon_from_raw(logo, M.CS_RGBA, 255) == 0
         batch = [jpegs[i % len(jpegs)] for i in range(args.file_images)]
-        capi.compose_batch(batch[:max(4 * threads, 256)], d, ALIGN_TOP_LEFT, 0, 0, 0, nthreads=threads)  # warm the page-locked slab (one full window)
+        capi.compose_batch((batch * 3)[:max(8 * threads, 512) + 8], d, ALIGN_TOP_LEFT, 0, 0, 0, nthreads=threads)  # warm both contexts' pools (two full windows and a bit)
         barrier()
         tm = {}
         rvb, status, outs = capi.compose_batch(batch, d, ALIGN_TOP_LEFT, 0, 0, 0, nthreads=threads, timing=tm)

@@ -21,6 +21,11 @@
 
 #include "mj_private.h"
 
+/* device buffers of a window in flight (pieces of the context's device scratch) */
+typedef struct {
+    void *planes, *segs, *sizes, *descs, *input, *dstatus;
+} devbufs_t;
+
 typedef struct {
     int            n;
     const mj_blob_t *in;
@@ -58,6 +63,8 @@ typedef struct {
     int             out_by_offset; /* phase 6: the slot's segment lies at seg_in_off[s], not at s * image_bytes */
     int             vrows[MJX_MAX_COMPONENTS];
     uint32_t       *dec_status;   /* per slot: K5's verdict (in the slab, behind seg_size) */
+    mjx_ctx        *ctx;          /* the context (stream, slab, device scratch) this window's device work was queued on */
+    devbufs_t       dv;
 } batch_t;
 
 static int take(batch_t *b, int limit) {
@@ -226,10 +233,6 @@ static int same_geometry(const mj_jpeg_t *a, const mj_jpeg_t *b) {
     return 1;
 }
 
-/* Device buffers of the device-resident path, kept across groups and windows */
-typedef struct {
-    void *planes, *segs, *sizes, *descs, *input, *dstatus;
-} devbufs_t;
 
 /* the device buffers of a window: one ctx-owned, grow-only scratch (it outlives the call: a server that sends batch after batch
  * allocates once), cut into the pieces a window needs */
@@ -356,8 +359,10 @@ static void group_finish(batch_t *b, mjx_ctx *ctx, devbufs_t *v, int nthreads, p
  *                         through the ordinary calls on the host (mj_read_jpeg_from_memory -> mj_compose -> mj_write_jpeg_to_memory)
  * Returns MJ_OK when queued; another code when the window is not of that kind (nothing was queued, the header-only objects are
  * freed) and the ordinary path has to read it. */
+static void finish_window(batch_t *w, mj_dropon_t *d, unsigned int align, int offset_x, int offset_y, int nthreads, pthread_t *th);
+
 static int window_enqueue_full(batch_t *b, mjx_ctx *ctx, devbufs_t *v, mjx_dropon **cd, mjx_layout_t *cd_layout, mjx_geometry_t *cd_g, mj_dropon_t *d,
-                               unsigned int align, int offset_x, int offset_y, int nthreads, pthread_t *th) {
+                               unsigned int align, int offset_x, int offset_y, int nthreads, pthread_t *th, batch_t **in_flight) {
     const int nw = b->w1 - b->w0;
     int       rv = MJ_OK, ref_k = -1;
     b->ngroup = 0;
@@ -385,6 +390,10 @@ static int window_enqueue_full(batch_t *b, mjx_ctx *ctx, devbufs_t *v, mjx_dropo
     if(rv == MJ_OK) rv = mjp_layout_of(ref, &layout);
     if(rv == MJ_OK && layout.ncomp > MJX_MAX_COMPONENTS) rv = MJ_ERR_UNSUPPORTED_FILETYPE;
     if(rv == MJ_OK && *cd != NULL && (memcmp(&layout, cd_layout, sizeof(layout)) != 0 || memcmp(&b->g, cd_g, sizeof(b->g)) != 0)) {
+        if(*in_flight != NULL) { /* the other window's blend still reads the compiled dropon */
+            finish_window(*in_flight, d, align, offset_x, offset_y, nthreads, th);
+            *in_flight = NULL;
+        }
         mjx_dropon_free(*cd);
         *cd = NULL;
     }
@@ -544,6 +553,15 @@ static void window_finish_full(batch_t *b, mjx_ctx *ctx, devbufs_t *v, mj_dropon
     b->full = 0;
 }
 
+/* collect a window whose device work is queued: files written, images freed */
+static void finish_window(batch_t *w, mj_dropon_t *d, unsigned int align, int offset_x, int offset_y, int nthreads, pthread_t *th) {
+    if(w->full) window_finish_full(w, w->ctx, &w->dv, d, align, offset_x, offset_y, nthreads, th);
+    else {
+        group_finish(w, w->ctx, &w->dv, nthreads, th);
+        run_phase(w, 4, nthreads, th); /* free; host encode of what the device handed back */
+    }
+}
+
 /* the pipeline on the calling thread's device */
 static int batch_on_device(int n, const mj_blob_t *in, mj_blob_t *out, int *status, mj_dropon_t *d, unsigned int align, int offset_x,
                            int offset_y, int write_options, int nthreads) {
@@ -586,52 +604,55 @@ static int batch_on_device(int n, const mj_blob_t *in, mj_blob_t *out, int *stat
     char      *done = (char *)malloc((size_t)window);
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
     mjx_host_image_t *items = (mjx_host_image_t *)malloc(sizeof(mjx_host_image_t) * (size_t)window);
-    devbufs_t      dv;
     mjx_dropon    *cd = NULL;
     mjx_layout_t   cd_layout;
     mjx_geometry_t cd_g;
-    batch_t       *pending = NULL; /* the window whose device work is queued and whose files are still to be written */
+    batch_t       *pend[2] = {NULL, NULL}; /* windows whose device work is queued and whose files are still to be written */
     int            cur = 0;
-    memset(&dv, 0, sizeof(dv));
+    mjx_ctx       *ctx2 = NULL;
     memset(&cd_layout, 0, sizeof(cd_layout));
     memset(&cd_g, 0, sizeof(cd_g));
     if(result != MJ_OK || done == NULL || th == NULL || items == NULL) {
         result = MJ_ERR_MEMORY;
         goto out;
     }
+    if(full_mode && n > window) ctx2 = mjp_host_ctx2(); /* (NULL: one window in flight) */
 
+    /* Two windows may be in flight: pend[k] = the window of state B[k] whose device work is queued.  Windows alternate between
+     * the states -- and, where the device decodes them, between the thread's two contexts, so that the device works on one
+     * window while the host collects the window before it and prepares the next. */
     for(int w0 = 0; w0 < n;) {
-        batch_t *bp = &B[cur];
+        const int si = cur;
+        batch_t  *bp = &B[si];
+        if(pend[si] != NULL) { /* two windows ago: its state, context and buffers are needed again */
+            finish_window(pend[si], d, align, offset_x, offset_y, nthreads, th);
+            pend[si] = NULL;
+        }
         bp->w0 = w0;
         bp->w1 = w0 + window < n ? w0 + window : n;
         w0 = bp->w1;
         if(full_mode) {
-            run_phase(bp, 7, nthreads, th); /* markers only -- the device works on the pending window meanwhile */
-            if(pending != NULL) {
-                if(pending->full) window_finish_full(pending, ctx, &dv, d, align, offset_x, offset_y, nthreads, th);
-                else {
-                    group_finish(pending, ctx, &dv, nthreads, th);
-                    run_phase(pending, 4, nthreads, th);
-                }
-                pending = NULL;
+            bp->ctx = (ctx2 != NULL && si == 1) ? ctx2 : ctx;
+            if(pend[si ^ 1] != NULL && pend[si ^ 1]->ctx == bp->ctx) { /* (one context only: one window in flight) */
+                finish_window(pend[si ^ 1], d, align, offset_x, offset_y, nthreads, th);
+                pend[si ^ 1] = NULL;
             }
+            run_phase(bp, 7, nthreads, th); /* markers only */
             memset(bp->written, 0, (size_t)window);
-            if(window_enqueue_full(bp, ctx, &dv, &cd, &cd_layout, &cd_g, d, align, offset_x, offset_y, nthreads, th) == MJ_OK) {
-                pending = bp;
+            if(window_enqueue_full(bp, bp->ctx, &bp->dv, &cd, &cd_layout, &cd_g, d, align, offset_x, offset_y, nthreads, th, &pend[si ^ 1]) == MJ_OK) {
+                pend[si] = bp;
                 cur ^= 1;
                 continue;
             }
             /* not a window of that kind: read it in full */
         }
-        run_phase(bp, 1, nthreads, th); /* entropy decode -- the device works on the pending window meanwhile */
-        if(pending != NULL) {
-            if(pending->full) window_finish_full(pending, ctx, &dv, d, align, offset_x, offset_y, nthreads, th);
-            else {
-                group_finish(pending, ctx, &dv, nthreads, th);
-                run_phase(pending, 4, nthreads, th); /* free; host encode of what the device handed back */
-            }
-            pending = NULL;
+        bp->ctx = ctx; /* the ordinary path lives on the thread's first context */
+        run_phase(bp, 1, nthreads, th); /* entropy decode -- the device works on the window before meanwhile */
+        if(pend[si ^ 1] != NULL) {
+            finish_window(pend[si ^ 1], d, align, offset_x, offset_y, nthreads, th);
+            pend[si ^ 1] = NULL;
         }
+        devbufs_t *const dvp = &bp->dv;
 
         /* compose the window group by group (images sharing one geometry share one compiled dropon and one launch) */
         memset(done, 0, (size_t)window);
@@ -668,12 +689,12 @@ static int batch_on_device(int n, const mj_blob_t *in, mj_blob_t *out, int *stat
             if(rv == MJ_OK && on_device) {
                 bp->ncomp = layout.ncomp;
                 bp->group = group;
-                if(group_enqueue(bp, ctx, &dv, cd, nthreads, th) == MJ_OK) {
+                if(group_enqueue(bp, ctx, dvp, cd, nthreads, th) == MJ_OK) {
                     /* the last group of the window is left running while the next window is decoded; a group with others
                      * behind it in this window is finished at once (its slab and device buffers are needed again) */
                     int more = 0;
                     for(int k = k0 + 1; k < bp->w1 - bp->w0; k++) more |= !done[k] && status[bp->w0 + k] == MJ_OK;
-                    if(more) group_finish(bp, ctx, &dv, nthreads, th);
+                    if(more) group_finish(bp, ctx, dvp, nthreads, th);
                     else deferred = 1;
                     continue;
                 }
@@ -725,18 +746,16 @@ static int batch_on_device(int n, const mj_blob_t *in, mj_blob_t *out, int *stat
                     if(status[group[s]] == MJ_OK) status[group[s]] = rv;
         }
         if(deferred) {
-            pending = bp; /* its files are written after the next window's decode */
+            bp->full = 0;
+            pend[si] = bp; /* its files are written after the next window's decode */
             cur ^= 1;
         }
         else run_phase(bp, 4, nthreads, th); /* entropy encode + free */
     }
-    if(pending != NULL) {
-        if(pending->full) window_finish_full(pending, ctx, &dv, d, align, offset_x, offset_y, nthreads, th);
-        else {
-            group_finish(pending, ctx, &dv, nthreads, th);
-            run_phase(pending, 4, nthreads, th);
-        }
-        pending = NULL;
+    for(int k = 0; k < 2; k++) { /* the older window first */
+        batch_t *w = pend[cur ^ k];
+        if(w != NULL) finish_window(w, d, align, offset_x, offset_y, nthreads, th);
+        pend[cur ^ k] = NULL;
     }
     if(getenv("MJ_BATCH_TRACE") != NULL) {
         double ps[9];
@@ -747,6 +766,7 @@ static int batch_on_device(int n, const mj_blob_t *in, mj_blob_t *out, int *stat
     }
 out:
     if(ctx != NULL) mjx_ctx_sync(ctx);
+    if(ctx2 != NULL) mjx_ctx_sync(ctx2);
     if(cd != NULL) mjx_dropon_free(cd);
     for(int k = 0; k < 2; k++) {
         free(B[k].jp);

@@ -38,6 +38,27 @@ mjx_ctx *mjx_host_ctx(void) {
     return ctx;
 }
 
+/* A second context of the calling thread on the same device (own stream, own staging pools): mj_compose_batch keeps two windows
+ * in flight, one per context.  NULL when it cannot be had -- the caller then works with one. */
+static pthread_key_t  g_key2;
+static pthread_once_t g_once2 = PTHREAD_ONCE_INIT;
+static void           ctx2_destructor(void *p) { mjx_ctx_destroy((mjx_ctx *)p); }
+static void           make_key2(void) { pthread_key_create(&g_key2, ctx2_destructor); }
+
+mjx_ctx *mjp_host_ctx2(void) {
+    if(mjx_host_ctx() == NULL) return NULL;
+    pthread_once(&g_once2, make_key2);
+    mjx_ctx *ctx = (mjx_ctx *)pthread_getspecific(g_key2);
+    if(ctx != NULL) return ctx;
+    int         device = 0;
+    const char *env = getenv("MJX_DEVICE");
+    if(t_device >= 0) device = t_device;
+    else if(env != NULL && *env) device = atoi(env);
+    if(mjx_ctx_create(&ctx, device) != MJX_OK || ctx == NULL) return NULL;
+    pthread_setspecific(g_key2, ctx);
+    return ctx;
+}
+
 /* The device the calling thread's context is created on (before its first compute call; a thread that already has a
  * context keeps it).  mj_compose_batch uses it to give each device its own group of host threads. */
 void mjx_host_set_device(int device) { t_device = device; }

@@ -55,6 +55,11 @@ int mj_read_jpeg_from_memory(mj_jpeg_t *m, const unsigned char *memory, size_t l
     }
     mjp_memsrc_init(src, memory, len);
     m->cinfo.src = &src->base;
+    /* mj_compose / mj_effect_* hand the kernels row pointers gathered from several access_virt_barray calls (the reference
+     * touches one row at a time).  That is sound only while libjpeg keeps whole arrays in memory -- always true for the
+     * malloc-only memory manager (jmemnobs, what libjpeg-turbo ships), and made true here for managers with a backing store,
+     * which would otherwise follow $JPEGMEM: no limit, no swapping of rows. */
+    m->cinfo.mem->max_memory_to_use = 0x3fffffffL * (long)(sizeof(long) > 4 ? 1024 : 1);
 
     /* keep COM and APP0..APP15 so that they can be written back (reference: src/image.c:67-72) */
     jpeg_save_markers(&m->cinfo, JPEG_COM, 0xFFFF);

@@ -73,6 +73,8 @@ int mjp_assemble_file(unsigned char **memory, size_t *len, const unsigned char *
 int mjp_read_header_only(mj_jpeg_t *m, const unsigned char *memory, size_t len, size_t *entropy_off, mjx_scan_t *scan);
 int mjp_layout_of(mj_jpeg_t *m, mjx_layout_t *layout);
 
+mjx_ctx *mjp_host_ctx2(void); /* a second context of the calling thread, same device (mj_device.c) */
+
 /* MJX_* -> MJ_* */
 int mjp_map_error(int mjx_rv);
 
