@@ -932,7 +932,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-kernels", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
-    ap.add_argument("--file-images", type=int, default=256, help="JPEGs pushed through mj_compose_batch (tier iii); 0 = skip")
+    ap.add_argument("--file-images", type=int, default=1024, help="JPEGs pushed through mj_compose_batch (tier iii); 0 = skip")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
