@@ -53,10 +53,13 @@ __global__ void __launch_bounds__(128) k2_op_prepare_kernel(const OpParams p) {
     __shared__ uint32_t s_q[MJX_MAX_COMPONENTS][32];
     __shared__ int      s_ok[MJX_MAX_COMPONENTS];
     const int           ncomp = p.drop.ncomp;
-    if(threadIdx.x < 32) {
-        for(int c = 0; c < ncomp; c++) {
-            const uint32_t w = reinterpret_cast<const uint32_t *>(&p.items[0].q[c][0])[threadIdx.x];
-            s_q[c][threadIdx.x] = w;
+    // warp c looks at component c of image 0 (the four chains of dependent loads run side by side: this launch sits in front of
+    // the operator kernel on every call)
+    {
+        const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if(c < ncomp) {
+            const uint32_t w = reinterpret_cast<const uint32_t *>(&p.items[0].q[c][0])[lane];
+            s_q[c][lane] = w;
             unsigned qm = max(w & 0xffffu, w >> 16), qn = min(w & 0xffffu, w >> 16);
             qm = __reduce_max_sync(0xffffffffu, qm);
             qn = __reduce_min_sync(0xffffffffu, qn);
@@ -64,12 +67,12 @@ __global__ void __launch_bounds__(128) k2_op_prepare_kernel(const OpParams p) {
             int sh = 9;
             while(sh > 0 && 1.01f * (float)qm * (float)(1 << sh) > 65000.0f) sh--;
             const int ok = (qm <= 255u && qn >= 1u) ? sh : -1;
-            if(threadIdx.x == 0) s_ok[c] = ok;
+            if(lane == 0) s_ok[c] = ok;
             if(blockIdx.x == 0) {
-                const uint32_t old = reinterpret_cast<const uint32_t *>(p.op.key + c * 64)[threadIdx.x];
+                const uint32_t old = reinterpret_cast<const uint32_t *>(p.op.key + c * 64)[lane];
                 const bool     differ = __any_sync(0xffffffffu, old != w);
-                reinterpret_cast<uint32_t *>(p.op.key + c * 64)[threadIdx.x] = w;
-                if(threadIdx.x == 0) {
+                reinterpret_cast<uint32_t *>(p.op.key + c * 64)[lane] = w;
+                if(lane == 0) {
                     p.op.rebuild[c] = differ ? 1 : 0;
                     p.op.info[c] = ok;
                 }
@@ -77,29 +80,30 @@ __global__ void __launch_bounds__(128) k2_op_prepare_kernel(const OpParams p) {
         }
     }
     __syncthreads();
-    const int i = blockIdx.x * 128 + threadIdx.x;
-    if(i >= p.n) return;
+    // one thread per (component, image)
+    const int idx = blockIdx.x * 128 + threadIdx.x;
+    if(idx >= p.n * ncomp) return;
+    const int               c = idx / p.n, i = idx - c * p.n;
     const mjx_image_desc_t &im = p.items[i];
     const int               ntiles = p.drop.n_generic >> 5;
-    for(int c = 0; c < ncomp; c++) {
-        const int t0 = p.drop.gtile_start[c], t1 = c + 1 < ncomp ? p.drop.gtile_start[c + 1] : ntiles;
-        bool      same = s_ok[c] >= 0;
-        if(same && i > 0) {
-            const uint4 *q = reinterpret_cast<const uint4 *>(&im.q[c][0]);
+    const int               t0 = p.drop.gtile_start[c], t1 = c + 1 < ncomp ? p.drop.gtile_start[c + 1] : ntiles;
+    bool                    same = s_ok[c] >= 0;
+    if(same && i > 0) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(&im.q[c][0]);
+        uint4        a[8];
 #pragma unroll
-            for(int k = 0; k < 8; k++) {
-                const uint4 a = __ldg(q + k);
-                same = same && a.x == s_q[c][4 * k] && a.y == s_q[c][4 * k + 1] && a.z == s_q[c][4 * k + 2] && a.w == s_q[c][4 * k + 3];
-            }
-        }
-        const unsigned long long plane = im.plane[c];
-        uint4                    t = make_uint4(0u, 0u, 0u, 0u);
-        if(same && plane != 0) t = make_uint4((uint32_t)plane, (uint32_t)(plane >> 32), (uint32_t)im.stride_blocks[c], (uint32_t)im.rows[c]);
-        p.table[(size_t)c * p.n + i] = t;
-        if(!same && plane != 0 && t1 > t0) {
-            for(int tl = t0; tl < t1; tl++) p.redo_mask[(size_t)tl * p.n + i] = 0xffffffffu;
-            atomicAdd(p.redo_count, 1u);
-        }
+        for(int k = 0; k < 8; k++) a[k] = __ldg(q + k);
+#pragma unroll
+        for(int k = 0; k < 8; k++)
+            same = same && a[k].x == s_q[c][4 * k] && a[k].y == s_q[c][4 * k + 1] && a[k].z == s_q[c][4 * k + 2] && a[k].w == s_q[c][4 * k + 3];
+    }
+    const unsigned long long plane = im.plane[c];
+    uint4                    t = make_uint4(0u, 0u, 0u, 0u);
+    if(same && plane != 0) t = make_uint4((uint32_t)plane, (uint32_t)(plane >> 32), (uint32_t)im.stride_blocks[c], (uint32_t)im.rows[c]);
+    p.table[(size_t)c * p.n + i] = t;
+    if(!same && plane != 0 && t1 > t0) {
+        for(int tl = t0; tl < t1; tl++) p.redo_mask[(size_t)tl * p.n + i] = 0xffffffffu;
+        atomicAdd(p.redo_count, 1u);
     }
 }
 
@@ -698,7 +702,7 @@ cudaError_t launch_k2_generic_op(cudaStream_t s, const OpParams &p, int sm_count
     cudaError_t e;
     const int   sms = sm_count > 0 ? sm_count : 148;
     if(p.op.np != 2) return cudaErrorInvalidValue;
-    k2_op_prepare_kernel<<<(p.n + 127) / 128, 128, 0, s>>>(p);
+    k2_op_prepare_kernel<<<(p.n * p.drop.ncomp + 127) / 128, 128, 0, s>>>(p);
     if((e = cudaGetLastError()) != cudaSuccess) return e;
     // one CTA per SM walks the slots; when the tables are unchanged every CTA leaves at once
     const int bctas = p.drop.n_generic < sms ? p.drop.n_generic : sms;
