@@ -125,13 +125,40 @@ __device__ __forceinline__ DecState unpack_state(uint2 u) {
     return s;
 }
 
-// one code word of table t at bit position p: symbol, and p moves behind it.  A bit pattern that is no code counts as a
-// 16-bit code for symbol 0 and raises *bad (a decoder in a wrong state may meet one; the right one never does in a valid file).
-__device__ __forceinline__ int decode_symbol(const DecTable &t, const uint32_t *words, uint32_t &p, int &bad) {
-    const uint32_t v = peek32(words, p);
+// Bit reader: the next 33..64 bits of the stream left-aligned in a 64-bit register, refilled one 32-bit word at a time -- one
+// load per 32 bits consumed instead of two per field looked at (the fields average 6 bits).
+struct BitReader {
+    const uint32_t    *words;
+    unsigned long long buf; // valid bits at the top
+    int                cnt; // how many (33..64 between fields)
+    uint32_t           wi;  // next word to load
+    __device__ __forceinline__ void start(const uint32_t *w, uint32_t p) {
+        words = w;
+        wi = p >> 5;
+        buf = ((unsigned long long)w[wi] << 32) | w[wi + 1];
+        buf <<= (p & 31u);
+        cnt = 64 - (int)(p & 31u);
+        wi += 2;
+    }
+    __device__ __forceinline__ uint32_t peek32() const { return (uint32_t)(buf >> 32); }
+    __device__ __forceinline__ void     skip(int n) {
+        buf <<= n;
+        cnt -= n;
+        if(cnt <= 32) {
+            buf |= (unsigned long long)words[wi++] << (32 - cnt);
+            cnt += 32;
+        }
+    }
+    __device__ __forceinline__ uint32_t pos() const { return wi * 32u - (uint32_t)cnt; }
+};
+
+// one code word of table t: symbol, and the reader moves behind it.  A bit pattern that is no code counts as a 16-bit code for
+// symbol 0 and raises bad (a decoder in a wrong state may meet one; the right one never does in a valid file).
+__device__ __forceinline__ int decode_symbol(const DecTable &t, BitReader &br, int &bad) {
+    const uint32_t v = br.peek32();
     const uint32_t e = t.look[v >> (32 - kLook)];
     if(e) {
-        p += e >> 8;
+        br.skip((int)(e >> 8));
         return (int)(e & 0xffu);
     }
     int l = kLook + 1;
@@ -142,10 +169,10 @@ __device__ __forceinline__ int decode_symbol(const DecTable &t, const uint32_t *
     }
     if(l > 16) {
         bad = 1;
-        p += 16;
+        br.skip(16);
         return 0;
     }
-    p += (uint32_t)l;
+    br.skip(l);
     return (int)t.vals[(code + t.valoff[l]) & 0xff];
 }
 
@@ -165,22 +192,25 @@ __device__ __forceinline__ uint32_t decode_run(const DecParams &p, const mjx_ima
         return reinterpret_cast<int16_t *>(im.plane[c]) + ((size_t)row * im.stride_blocks[c] + col) * 64;
     };
     if(kWrite) dst = locate(blk);
-    while(s.p < end) {
+    if(s.p >= end) return 0;
+    BitReader br;
+    br.start(words, s.p);
+    do {
         const int c = p.bcomp[s.b];
         if(s.z == 0) {
-            const int sym = decode_symbol(tab[p.dc_tbl[c]], words, s.p, s.bad);
+            const int sym = decode_symbol(tab[p.dc_tbl[c]], br, s.bad);
             const int n = sym & 15;
             if(sym > 15) s.bad = 1;
             int diff = 0;
             if(n) {
-                diff = extend(peek32(words, s.p) >> (32 - n), n);
-                s.p += (uint32_t)n;
+                diff = extend(br.peek32() >> (32 - n), n);
+                br.skip(n);
             }
             if(kWrite && dst) dst[0] = (int16_t)diff;
             s.z = 1;
         }
         else {
-            const int sym = decode_symbol(tab[4 + p.ac_tbl[c]], words, s.p, s.bad);
+            const int sym = decode_symbol(tab[4 + p.ac_tbl[c]], br, s.bad);
             const int r = sym >> 4, n = sym & 15;
             if(n == 0) {
                 if(r == 15) {
@@ -193,8 +223,8 @@ __device__ __forceinline__ uint32_t decode_run(const DecParams &p, const mjx_ima
                 s.z += r;
                 if(s.z > 63) s.bad = 1, s.z = 64;
                 else {
-                    const int val = extend(peek32(words, s.p) >> (32 - n), n);
-                    s.p += (uint32_t)n;
+                    const int val = extend(br.peek32() >> (32 - n), n);
+                    br.skip(n);
                     if(kWrite && dst) dst[c_natural[s.z]] = (int16_t)val;
                     s.z++;
                 }
@@ -209,7 +239,8 @@ __device__ __forceinline__ uint32_t decode_run(const DecParams &p, const mjx_ima
                 dst = locate(blk + done);
             }
         }
-    }
+    } while(br.pos() < end);
+    s.p = br.pos();
     return done;
 }
 
