@@ -56,7 +56,7 @@ struct DecParams {
     int                     ncomp, blocks_per_mcu, mcus_per_row, mcu_rows, nblk;
     int                     h[MJX_MAX_COMPONENTS], v[MJX_MAX_COMPONENTS];
     int                     dc_tbl[MJX_MAX_COMPONENTS], ac_tbl[MJX_MAX_COMPONENTS];
-    signed char             bcomp[16], bidx[16];
+    signed char             bcomp[16], bidx[16], byoff[16], bxoff[16]; // per block of the MCU: component, index in it, row / column offset
     const DecTable         *tables; // [8]: 0..3 DC, 4..7 AC
     uint32_t               *words;  // [n][words_stride] un-stuffed stream
     size_t                  words_stride;
@@ -131,7 +131,8 @@ struct BitReader {
     const uint32_t    *words;
     unsigned long long buf; // valid bits at the top
     int                cnt; // how many (33..64 between fields)
-    uint32_t           wi;  // next word to load
+    uint32_t           wi;  // index of `nxt`
+    uint32_t           nxt; // the word the next refill will use, loaded a refill ahead so that nobody waits for it
     __device__ __forceinline__ void start(const uint32_t *w, uint32_t p) {
         words = w;
         wi = p >> 5;
@@ -139,14 +140,16 @@ struct BitReader {
         buf <<= (p & 31u);
         cnt = 64 - (int)(p & 31u);
         wi += 2;
+        nxt = w[wi];
     }
     __device__ __forceinline__ uint32_t peek32() const { return (uint32_t)(buf >> 32); }
     __device__ __forceinline__ void     skip(int n) {
         buf <<= n;
         cnt -= n;
         if(cnt <= 32) {
-            buf |= (unsigned long long)words[wi++] << (32 - cnt);
+            buf |= (unsigned long long)nxt << (32 - cnt);
             cnt += 32;
+            nxt = words[++wi];
         }
     }
     __device__ __forceinline__ uint32_t pos() const { return wi * 32u - (uint32_t)cnt; }
@@ -183,15 +186,22 @@ __device__ __forceinline__ uint32_t decode_run(const DecParams &p, const mjx_ima
                                                uint32_t blk) {
     uint32_t done = 0;
     int16_t *dst = nullptr;
-    auto     locate = [&](uint32_t k) -> int16_t * { // block k of the scan; past the frame: nowhere
-        if(k >= (uint32_t)p.nblk) return nullptr;
-        const int mcu = (int)(k / (uint32_t)p.blocks_per_mcu), bi = (int)(k - (uint32_t)mcu * p.blocks_per_mcu);
-        const int c = p.bcomp[bi], kk = p.bidx[bi], mrow = mcu / p.mcus_per_row, mcol = mcu - mrow * p.mcus_per_row;
-        const int row = mrow * p.v[c] + kk / p.h[c], col = mcol * p.h[c] + kk % p.h[c];
+    // where block `blk` lies: MCU (mrow, mcol), block bi of it -- divisions once per subsequence, then counted along
+    int  bi = 0, mrow = 0, mcol = 0;
+    auto locate = [&]() -> int16_t * {
+        const int c = p.bcomp[bi], kk = p.bidx[bi];
+        const int row = mrow * p.v[c] + p.byoff[bi], col = mcol * p.h[c] + p.bxoff[bi];
+        (void)kk;
         if(row >= im.rows[c] || col >= im.stride_blocks[c]) return nullptr;
         return reinterpret_cast<int16_t *>(im.plane[c]) + ((size_t)row * im.stride_blocks[c] + col) * 64;
     };
-    if(kWrite) dst = locate(blk);
+    if(kWrite) {
+        const int mcu = (int)(blk / (uint32_t)p.blocks_per_mcu);
+        bi = (int)(blk - (uint32_t)mcu * p.blocks_per_mcu);
+        mrow = mcu / p.mcus_per_row;
+        mcol = mcu - mrow * p.mcus_per_row;
+        dst = blk < (uint32_t)p.nblk ? locate() : nullptr;
+    }
     if(s.p >= end) return 0;
     BitReader br;
     br.start(words, s.p);
@@ -236,7 +246,11 @@ __device__ __forceinline__ uint32_t decode_run(const DecParams &p, const mjx_ima
             done++;
             if(kWrite) {
                 if(blk + done >= (uint32_t)p.nblk) break; // the frame's last block: what follows (padding bits, EOI) is not ours
-                dst = locate(blk + done);
+                if(++bi == p.blocks_per_mcu) {
+                    bi = 0;
+                    if(++mcol == p.mcus_per_row) mcol = 0, mrow++;
+                }
+                dst = locate();
             }
         }
     } while(br.pos() < end);
@@ -269,12 +283,22 @@ __global__ void __launch_bounds__(kDecThreads) k5_decode_kernel(const DecParams 
     {
         const uint32_t piece = (len + kDecThreads - 1) / kDecThreads, lo = min(len, (uint32_t)tid * piece), hi = min(len, lo + piece);
         uint32_t       keep = 0;
-        for(uint32_t i = lo; i < hi; i++) keep += !(src[i] == 0 && i > 0 && src[i - 1] == 0xff);
-        uint32_t at = (uint32_t)cta_exclusive_scan(keep, s_warp, &total);
+        unsigned       prev = lo > 0 ? src[lo - 1] : 0u;
+#pragma unroll 4
         for(uint32_t i = lo; i < hi; i++) {
-            const unsigned char b = src[i];
-            if(b == 0 && i > 0 && src[i - 1] == 0xff) continue;
-            wbytes[at ^ 3u] = b; // big-endian inside each 32-bit word
+            const unsigned b = src[i];
+            keep += !(b == 0u && prev == 0xffu);
+            prev = b;
+        }
+        uint32_t at = (uint32_t)cta_exclusive_scan(keep, s_warp, &total);
+        prev = lo > 0 ? src[lo - 1] : 0u;
+#pragma unroll 4
+        for(uint32_t i = lo; i < hi; i++) {
+            const unsigned b = src[i];
+            const bool     drop = b == 0u && prev == 0xffu;
+            prev = b;
+            if(drop) continue;
+            wbytes[at ^ 3u] = (unsigned char)b; // big-endian inside each 32-bit word
             at++;
         }
         // zeros behind the end: a bit window may reach 8 bytes past it
@@ -445,6 +469,7 @@ int mjx_huffman_decode_batch_device(mjx_ctx *ctx, const void *data_dev, const ui
         for(int k = 0; k < h * v; k++) {
             if(bpm >= 10) return MJX_ERR_UNSUPPORTED; // D_MAX_BLOCKS_IN_MCU
             p.bcomp[bpm] = (signed char)c, p.bidx[bpm] = (signed char)k;
+            p.byoff[bpm] = (signed char)(k / h), p.bxoff[bpm] = (signed char)(k % h);
             bpm++;
         }
     }
