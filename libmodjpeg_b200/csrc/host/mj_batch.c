@@ -579,8 +579,12 @@ static int batch_on_device(int n, const mj_blob_t *in, mj_blob_t *out, int *stat
         if(e != NULL && *e == '0') full_mode = 0;
     }
     int window = 4 * nthreads;
-    if(full_mode && window < 256) window = 256; /* one CTA per image decodes: the device wants a few hundred images at a time */
     if(window > 256) window = 256;
+    if(full_mode && window < 256) window = 256; /* one CTA per image decodes: the device wants a few hundred images at a time */
+    {
+        const char *e = getenv("MJX_BATCH_WINDOW"); /* images per window (16 .. 4096) */
+        if(e != NULL && atoi(e) >= 16 && atoi(e) <= 4096) window = atoi(e);
+    }
     if(window > n) window = n;
     /* two window states: while the device works on one window (queued by group_enqueue), the pool decodes the next */
     batch_t B[2];
