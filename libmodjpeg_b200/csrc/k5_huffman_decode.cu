@@ -16,7 +16,7 @@
 //      exact for t = 0, a guess (block start of the MCU's first block) for the others.  ROUNDS: every subsequence whose
 //      entry state changed is decoded (no output) and its exit state becomes the entry state of the next one.  When a round
 //      changes nothing, every entry state is exact by induction from t = 0 -- no probabilistic argument is involved, only
-//      the NUMBER of rounds depends on how fast the codes synchronise (2 - 6 on photographs);
+//      the NUMBER of rounds depends on how fast the codes synchronise (3 on the bench's 1080p files);
 //   3. prefix sum of the blocks each subsequence completes -> index of the block a subsequence starts in;
 //   4. every subsequence is decoded once more, now writing its coefficients (de-zigzagged) into the planes; the DC slot
 //      receives the DIFFERENCE;
@@ -189,9 +189,8 @@ __device__ __forceinline__ uint32_t decode_run(const DecParams &p, const mjx_ima
     // where block `blk` lies: MCU (mrow, mcol), block bi of it -- divisions once per subsequence, then counted along
     int  bi = 0, mrow = 0, mcol = 0;
     auto locate = [&]() -> int16_t * {
-        const int c = p.bcomp[bi], kk = p.bidx[bi];
+        const int c = p.bcomp[bi];
         const int row = mrow * p.v[c] + p.byoff[bi], col = mcol * p.h[c] + p.bxoff[bi];
-        (void)kk;
         if(row >= im.rows[c] || col >= im.stride_blocks[c]) return nullptr;
         return reinterpret_cast<int16_t *>(im.plane[c]) + ((size_t)row * im.stride_blocks[c] + col) * 64;
     };
