@@ -280,26 +280,36 @@ __global__ void __launch_bounds__(kDecThreads) k5_decode_kernel(const DecParams 
 
     // ---- 1. un-stuff ----
     {
-        const uint32_t piece = (len + kDecThreads - 1) / kDecThreads, lo = min(len, (uint32_t)tid * piece), hi = min(len, lo + piece);
+        // every thread a piece of whole 16-byte chunks; a segment that starts on a 16-byte boundary (the batch pipeline's do) is
+        // read 128 bits at a time, any other byte by byte
+        const uint32_t piece = (((len + kDecThreads - 1) / kDecThreads) + 15u) & ~15u, lo = min(len, (uint32_t)tid * piece), hi = min(len, lo + piece);
+        const bool     vec = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
         uint32_t       keep = 0;
         unsigned       prev = lo > 0 ? src[lo - 1] : 0u;
-#pragma unroll 4
-        for(uint32_t i = lo; i < hi; i++) {
-            const unsigned b = src[i];
-            keep += !(b == 0u && prev == 0xffu);
-            prev = b;
-        }
-        uint32_t at = (uint32_t)cta_exclusive_scan(keep, s_warp, &total);
-        prev = lo > 0 ? src[lo - 1] : 0u;
-#pragma unroll 4
-        for(uint32_t i = lo; i < hi; i++) {
-            const unsigned b = src[i];
-            const bool     drop = b == 0u && prev == 0xffu;
-            prev = b;
-            if(drop) continue;
-            wbytes[at ^ 3u] = (unsigned char)b; // big-endian inside each 32-bit word
-            at++;
-        }
+        // kCount: how many bytes stay; otherwise: put them where they belong
+        auto pass = [&](const bool count, uint32_t at) -> uint32_t {
+            unsigned pv = prev;
+            uint32_t i = lo;
+            auto     one = [&](unsigned b) {
+                const bool drop = b == 0u && pv == 0xffu;
+                pv = b;
+                if(drop) return;
+                if(!count) wbytes[at ^ 3u] = (unsigned char)b; // big-endian inside each 32-bit word
+                at++;
+            };
+            if(vec)
+                for(; i + 16 <= hi; i += 16) {
+                    const uint4    q = __ldg(reinterpret_cast<const uint4 *>(src + i));
+                    const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for(int k = 0; k < 16; k++) one((w4[k >> 2] >> (8 * (k & 3))) & 0xffu);
+                }
+            for(; i < hi; i++) one(src[i]);
+            return at;
+        };
+        keep = pass(true, 0u);
+        const uint32_t at0 = (uint32_t)cta_exclusive_scan(keep, s_warp, &total);
+        pass(false, at0);
         // zeros behind the end: a bit window may reach 8 bytes past it
         const uint32_t nbytes = (uint32_t)total;
         if(tid < 16) wbytes[(nbytes + (uint32_t)tid) ^ 3u] = 0;
