@@ -555,6 +555,24 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
 
     ms_simple = time_masked(1) if counts["OPAQUE"] + counts["U"] else 0.0
     ms_generic = time_masked(2) if counts["G"] else 0.0
+    # the other two ways the G class can run, timed in the same process right behind (reported under roofline.alternatives;
+    # the headline numbers above are the library's default)
+    alternatives = {}
+    if counts["G"] and rank == 0 and engine.tensor_core_active(n, counts["G"]):
+        default_mode = getattr(engine, "_tc_mode", 1)
+        for name, mode in (("tensor_core_range_vouched", 2), ("fp32_kernel", 0)):
+            if mode == default_mode:
+                continue
+            try:
+                engine.set_tensor_core(mode)
+                g_ms = time_masked(2)
+                s_ms = time_masked(3)
+                alternatives[name] = {"mode": mode, "g_kernel_ms": g_ms, "step_ms": s_ms}
+            finally:
+                engine.set_tensor_core(default_mode)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize(dev)
     # clocks / throttle reasons sampled from just before the timed steps to the end of the per-kernel timings
     # (the same kernels back to back: the GPU is under the bench's load for the whole window)
     if rank == 0:
@@ -893,7 +911,10 @@ def run_b200_arm(args, rank: int, local_rank: int, world: int):
                          "step": {"achieved": achieved, "frac": achieved / peak, "algorithmic_bytes": alg_bytes, "ms": launch_ms,
                                   "what": "whole K2 step = the G-class kernel, then k2_simple_kernel (the operator kernel fills every SM's shared memory, so the two run one after the other; "
                                           "with the fp32 G kernel the simple kernel runs beside it on a side stream)"},
-                         "kernels": kernels},
+                         "kernels": kernels,
+                         "alternatives": {k: dict(v, g_kernel_frac=alg_generic / (v["g_kernel_ms"] * 1e-3) / 1e9 / peak,
+                                                  step_frac=alg_bytes / (v["step_ms"] * 1e-3) / 1e9 / peak,
+                                                  value_mblocks_per_s=n * blocks_per_image / (v["step_ms"] * 1e-3) / 1e6) for k, v in alternatives.items()}},
             "parity": parity,
             "per_image_compile_and_blend": per_image,
             "other_kernels": other,
