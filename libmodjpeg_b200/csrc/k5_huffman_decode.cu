@@ -433,6 +433,7 @@ static bool derive_dec_table(const mjx_huff_table_t &t, DecTable *d) {
         if(cnt) {
             d->valoff[l] = k - code;
             for(int i = 0; i < cnt; i++, k++, code++) {
+                if(code >= (1 << l)) return false; // more codes of this length than there are bit patterns: not a Huffman table
                 if(l <= kLook) { // every kLook-bit pattern that starts with this code
                     const int fill = 1 << (kLook - l);
                     for(int f = 0; f < fill; f++) d->look[(code << (kLook - l)) | f] = (uint16_t)((l << 8) | t.vals[k]);
