@@ -173,15 +173,39 @@ __device__ __forceinline__ void load_block(const mjx_image_desc_t &im, const Blo
 template <bool kEmit>
 __global__ void __launch_bounds__(kHuffThreads) k4_block_kernel(const HuffParams p) {
     __shared__ uint32_t s_tab[8 * 256];
+    // the CTA's blocks pass through shared memory: a warp fetches its 32 blocks with eight instructions that each take whole
+    // 128-byte lines (8 lanes per block), then every thread picks up its own block -- a thread reading its 128 bytes from
+    // global memory by itself costs 32 lines per instruction.  One 16-byte chunk of padding per block keeps both sides free of
+    // bank conflicts.
+    __shared__ uint4 s_blk[kHuffThreads * 9];
     for(int i = threadIdx.x; i < 8 * 256; i += kHuffThreads) s_tab[i] = __ldg(p.tables + i);
     __syncthreads();
     const int img = blockIdx.y, t = blockIdx.x * kHuffThreads + threadIdx.x;
-    if(t >= p.nblk) return;
-    if(kEmit && p.status[img] != 0u) return;
+    if(kEmit && p.status[img] != 0u) return; // (the whole CTA: one image per blockIdx.y)
     const mjx_image_desc_t &im = p.items[img];
-    const BlockPos          b = block_pos(p, im, t);
-    uint32_t                w[32];
-    load_block(im, b, w);
+    const bool              valid = t < p.nblk;
+    BlockPos                b;
+    if(valid) b = block_pos(p, im, t);
+    else b.c = 0, b.row = b.col = b.mrow = b.mcol = b.k = 0, b.real = false;
+    uint32_t w[32];
+    {
+        const int                lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+        const unsigned long long mine = b.real ? (unsigned long long)(uintptr_t)block_ptr(im, b.c, b.row, b.col) : 0ull;
+#pragma unroll
+        for(int i = 0; i < 8; i++) {
+            const int                sl = 4 * i + (lane >> 3);
+            const unsigned long long q = __shfl_sync(0xffffffffu, mine, sl);
+            const uint4              x = q ? __ldg(reinterpret_cast<const uint4 *>(q) + (lane & 7)) : make_uint4(0u, 0u, 0u, 0u);
+            s_blk[(wbase + sl) * 9 + (lane & 7)] = x;
+        }
+        __syncwarp();
+#pragma unroll
+        for(int i = 0; i < 8; i++) {
+            const uint4 x = s_blk[threadIdx.x * 9 + i];
+            w[4 * i] = x.x, w[4 * i + 1] = x.y, w[4 * i + 2] = x.z, w[4 * i + 3] = x.w;
+        }
+    }
+    if(!valid) return;
     int diff = 0;
     if(b.real) diff = (int)(short)(w[0] & 0xffffu) - predecessor_dc(p, im, b);
     const uint32_t *dct = s_tab + 256 * p.dc_tbl[b.c], *act = s_tab + 256 * (4 + p.ac_tbl[b.c]);
