@@ -247,44 +247,55 @@ __global__ void __launch_bounds__(kScanThreads) k4_scan_kernel(uint32_t *data, s
     // m: either fixed, or derived from another per-image total (the stream's pieces: (bits + 7) / 8 bytes in 64-byte pieces)
     int m = m_fixed;
     if(count_src) {
+        // an image that is not being coded (its stream would not fit the slab, or a coefficient cannot be coded) has no pieces
+        // to count -- and its bit total may describe more pieces than its row holds
+        if(status[img] != 0u) return;
         const unsigned long long nbytes = ((unsigned long long)count_src[img] + 7ull) >> 3;
         m = (int)((nbytes + (1ull << count_shift) - 1ull) >> count_shift);
     }
-    uint32_t *d = data + (size_t)img * stride;
-    const int chunk = (m + kScanThreads - 1) / kScanThreads;
-    const int lo = min(m, (int)threadIdx.x * chunk), hi = min(m, lo + chunk);
-    unsigned long long s = 0;
-    for(int i = lo; i < hi; i++) s += d[i];
-    // inclusive scan over the CTA's partial sums
-    unsigned long long x = s;
+    if((size_t)m > stride) m = (int)stride;
+    // tiles of 4 x kScanThreads values: every thread four consecutive ones (one 128-bit access each way), a CTA-wide scan of
+    // the threads' sums per tile, the running total carried from tile to tile (the rows are padded to multiples of 64 values,
+    // so a whole 128-bit access never leaves the row; what lies behind m counts as zero)
+    uint4             *d4 = reinterpret_cast<uint4 *>(data + (size_t)img * stride);
     const int          lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for(int o = 1; o < 32; o <<= 1) {
-        const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
-        if(lane >= o) x += y;
-    }
-    if(lane == 31) s_warp[warp] = x;
-    __syncthreads();
-    if(warp == 0) {
-        unsigned long long y = s_warp[lane];
+    unsigned long long carry = 0;
+    for(int base = 0; base < m; base += 4 * kScanThreads) {
+        const int i0 = base + 4 * (int)threadIdx.x;
+        uint4     v = make_uint4(0u, 0u, 0u, 0u);
+        if(i0 < m) {
+            v = d4[i0 >> 2];
+            if(i0 + 1 >= m) v.y = 0u;
+            if(i0 + 2 >= m) v.z = 0u;
+            if(i0 + 3 >= m) v.w = 0u;
+        }
+        const unsigned long long s = (unsigned long long)v.x + v.y + v.z + v.w;
+        unsigned long long       x = s;
 #pragma unroll
         for(int o = 1; o < 32; o <<= 1) {
-            const unsigned long long z = __shfl_up_sync(0xffffffffu, y, o);
-            if(lane >= o) y += z;
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+            if(lane >= o) x += y;
         }
-        s_warp[lane] = y;
+        __syncthreads(); // (s_warp of the previous tile has been read)
+        if(lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if(warp == 0) {
+            unsigned long long y = s_warp[lane];
+#pragma unroll
+            for(int o = 1; o < 32; o <<= 1) {
+                const unsigned long long z = __shfl_up_sync(0xffffffffu, y, o);
+                if(lane >= o) y += z;
+            }
+            s_warp[lane] = y;
+        }
+        __syncthreads();
+        const unsigned long long run = carry + x - s + (warp > 0 ? s_warp[warp - 1] : 0ull);
+        if(i0 < m) d4[i0 >> 2] = make_uint4((uint32_t)run, (uint32_t)(run + v.x), (uint32_t)(run + v.x + v.y), (uint32_t)(run + v.x + v.y + v.z));
+        carry += s_warp[kScanThreads / 32 - 1];
     }
-    __syncthreads();
-    unsigned long long run = x - s + (warp > 0 ? s_warp[warp - 1] : 0ull);
-    for(int i = lo; i < hi; i++) {
-        const uint32_t v = d[i];
-        d[i] = (uint32_t)run;
-        run += v;
-    }
-    if(threadIdx.x == kScanThreads - 1) {
-        const unsigned long long total = s_warp[kScanThreads / 32 - 1];
-        totals[img] = total > 0xffffffffull ? 0xffffffffu : (uint32_t)total;
-        if(total > limit) atomicOr(status + img, 2u);
+    if(threadIdx.x == 0) {
+        totals[img] = carry > 0xffffffffull ? 0xffffffffu : (uint32_t)carry;
+        if(carry > limit) atomicOr(status + img, 2u);
     }
 }
 
