@@ -173,3 +173,18 @@ def test_damaged_files_do_not_bring_the_pipeline_down(engine):
         j = M.Jpeg()
         assert j.read_jpeg_from_memory(good[i]) == 0 and j.compose(d, M.ALIGN_CENTER, 0, 0) == 0
         assert j.write_jpeg_to_memory(0)[1] == outs[i], i
+
+
+def test_batch_pipeline_random_sweep(engine):
+    """profiles/fuzz_batch.py in small: random sizes / samplings / qualities, batches of one geometry (all-device path) and mixed
+    ones (progressive, optimised, grayscale, damaged inputs) -- every file mj_compose_batch writes equals the per-image calls'"""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    out = subprocess.run([sys.executable, os.path.join(root, "profiles", "fuzz_batch.py"), "160", "31"], check=True, capture_output=True, text=True).stdout
+    rep = json.loads(out)
+    assert rep["images"] >= 160 and rep["mismatches"] == 0 and rep["status_mismatches"] == 0
+    assert any(b["uniform"] for b in rep["batches"]) and any(not b["uniform"] for b in rep["batches"])
