@@ -14,6 +14,8 @@
 //   k4_stuff_kernel<false>  thread per 64 bytes of the stream: bytes equal to 0xFF (each needs a stuffed 0x00 behind it)
 //   k4_scan_kernel          again: output position of every 64-byte piece
 //   k4_stuff_kernel<true>   the bytes, stuffed, at their final place; the last byte padded with 1-bits (jchuff.c flush_bits)
+// A warp fetches its 32 blocks in whole 128-byte lines and hands them to their threads through shared memory; the scans move
+// 128 bits per access.
 // Blocks past a component's real width / height (the MCU grid is rounded up) are the encoder's dummy blocks: no AC, DC
 // equal to the previous block's, i.e. a zero difference (jctrans.c compress_output) -- whatever the plane holds there.
 // The result is byte-identical to libjpeg's entropy-coded segment (tests/test_gpu_huffman.py compares whole files with
