@@ -17,6 +17,11 @@ resident in HBM (7.8 GB per GPU >> 126 MB L2, so no L2 flush is needed between s
            measured copy bandwidth in MEASURED_PEAKS.json.
 `cpu_baseline` = the unmodified reference (oracle/_ref, mj_compose incl. its dropon compile) on
            the box's host cores, on a bounded sample of the same images.
+`roofline.alternatives` = the G class on the range-vouched tensor-core kernel and on the fp32 kernel, same run.
+`parity`  = 8 images of the timed batch against oracle/_ref (outside every timed region).
+`other_kernels` = K1, K3, K4 (Huffman coding) and K5 (Huffman decoding) on the same resident batch.
+`e2e_files` = mj_compose_batch: JPEG bytes in -> JPEG bytes out (K5, K1, K2, K4 on the device), and the unmodified
+           reference's read -> compose -> write loop on the same host threads.
 `--impl reference` times only that CPU arm and prints the same line shape.
 """
 from __future__ import annotations
